@@ -1,0 +1,228 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the REAL reference.
+
+Run in the build container only (it imports ekzhu/datasketch from
+/root/reference, which does not exist on the GPU box):
+
+    python oracle/gen_golden.py
+
+Every array written here is an output of the unmodified reference's public API
+(``MinHash``, ``LeanMinHash``, ``WeightedMinHashGenerator``, ``MinHashLSH``) on
+the seeded inputs stored next to it, so the fixtures pin both the oracle
+(oracle/oracle_np.py, oracle/oracle_c.c) and the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("DATASKETCH_REF", "/root/reference")
+sys.path.insert(0, REF)
+import datasketch  # noqa: E402  (the reference)
+from datasketch import LeanMinHash, MinHash, MinHashLSH, WeightedMinHashGenerator  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def ident(x):
+    return int(x)
+
+
+def ragged(rs, n, maxlen, hi=2 ** 32, dtype=np.uint64):
+    lens = rs.randint(0, maxlen + 1, size=n)
+    lens[:3] = [0, 1, 2]            # empty / single / pair documents
+    lens[-1] = 0                    # trailing empty document
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, hi, size=int(off[-1]), dtype=dtype)
+    return tok, off
+
+
+def ref_bulk(tok, off, **kw):
+    docs = [[int(x) for x in tok[off[i]:off[i + 1]]] for i in range(len(off) - 1)]
+    ms = MinHash.bulk(docs, hashfunc=ident, **kw)
+    return np.stack([m.hashvalues for m in ms]) if ms else np.zeros((0, kw["num_perm"]), np.uint64)
+
+
+def gen_minhash():
+    d = {}
+    # the reference's own absolute golden (test/test_minhash.py:109-115)
+    m = MinHash(4, 1)
+    m.update(b"Hello")
+    d["hello_k4_seed1"] = m.hashvalues.copy()
+    # permutations (minhash.py:170-184)
+    for k, seed in [(4, 1), (128, 1), (256, 7), (100, 42)]:
+        d[f"perm_k{k}_s{seed}"] = MinHash(num_perm=k, seed=seed).permutations
+    # C1: 1000 docs x 64 tokens, K=128, seed=1 (BASELINE.json configs[0])
+    rs = np.random.RandomState(0)
+    tok = rs.randint(0, 2 ** 32, size=(1000, 64), dtype=np.uint64)
+    d["c1_tokens"] = tok.astype(np.uint32)
+    off = np.arange(1001, dtype=np.int64) * 64
+    sig = ref_bulk(tok.reshape(-1), off, num_perm=128, seed=1)
+    assert sig.max() < 2 ** 32
+    d["c1_sig"] = sig.astype(np.uint32)
+    # ragged batches incl. empty docs, several K / seeds
+    for k, seed in [(4, 1), (100, 42), (128, 1), (256, 7), (33, 5)]:
+        rs = np.random.RandomState(100 + k)
+        tok, off = ragged(rs, 120, 300)
+        d[f"rag_k{k}_tokens"] = tok.astype(np.uint32)
+        d[f"rag_k{k}_offsets"] = off
+        d[f"rag_k{k}_seed"] = np.int64(seed)
+        d[f"rag_k{k}_sig"] = ref_bulk(tok, off, num_perm=k, seed=seed).astype(np.uint32)
+    # a long document (T >> K) and tiny-hash tokens (small ints as in test/utils.py fake_hash_func)
+    rs = np.random.RandomState(7)
+    tok = rs.randint(0, 2 ** 32, size=20000, dtype=np.uint64)
+    off = np.array([0, 20000], dtype=np.int64)
+    d["long_tokens"] = tok.astype(np.uint32)
+    d["long_sig"] = ref_bulk(tok, off, num_perm=128, seed=1).astype(np.uint32)
+    small = np.arange(0, 64, dtype=np.uint64) * 4
+    d["small_tokens"] = small.astype(np.uint32)
+    d["small_sig"] = ref_bulk(small, np.array([0, 64], np.int64), num_perm=128, seed=1).astype(np.uint32)
+    # default SHA1 hashfunc on byte tokens (test/test_minhash_gpu.py:20-52 shapes)
+    data = [f"token-{i}".encode("utf-8") for i in range(1000)]
+    m = MinHash(num_perm=256, seed=7)
+    m.update_batch(data)
+    d["sha1_k256_s7_n1000"] = m.hashvalues.copy()
+    m = MinHash(num_perm=128, seed=7)
+    m.update_batch(data[:500])
+    m.update_batch([f"token-{i}".encode("utf-8") for i in range(700)])
+    d["sha1_k128_s7_500_700"] = m.hashvalues.copy()
+    # hash values wider than 32 bits (minhash.py:294 casts to uint64)
+    rs = np.random.RandomState(11)
+    tok, off = ragged(rs, 40, 50, hi=2 ** 63, dtype=np.uint64)
+    tok[::3] |= np.uint64(1) << np.uint64(63)
+    tok[1::5] = rs.randint(2 ** 32, 2 ** 40, size=len(tok[1::5]), dtype=np.uint64)
+    d["u64_tokens"] = tok
+    d["u64_offsets"] = off
+    d["u64_sig"] = ref_bulk(tok, off, num_perm=64, seed=3)
+    # update_batch on a non-empty state, then jaccard / merge / union
+    m1 = MinHash(num_perm=128, seed=1, hashfunc=ident)
+    m1.update_batch(range(0, 300))
+    m2 = MinHash(num_perm=128, seed=1, hashfunc=ident)
+    m2.update_batch(range(150, 450))
+    d["j_m1"], d["j_m2"] = m1.hashvalues.copy(), m2.hashvalues.copy()
+    d["j_jaccard"] = np.float64(m1.jaccard(m2))
+    d["j_count1"] = np.float64(m1.count())
+    mm = m1.copy()
+    mm.merge(m2)
+    d["j_merge"] = mm.hashvalues.copy()
+    d["j_union"] = MinHash.union(m1, m2).hashvalues.copy()
+    np.savez_compressed(os.path.join(OUT, "minhash.npz"), **d)
+
+
+def gen_lean():
+    d = {}
+    m = MinHash(10, 1, hashfunc=ident)
+    m.update(123)
+    lm = LeanMinHash(m)
+    d["hashvalues"] = lm.hashvalues.copy()
+    d["seed"] = np.int64(lm.seed)
+    names = {"@": "native", "=": "std", "<": "le", ">": "be", "!": "net"}
+    for bo, nm in names.items():
+        buf = bytearray(lm.bytesize(bo))
+        lm.serialize(buf, bo)
+        d[f"buf_{nm}"] = np.frombuffer(bytes(buf), dtype=np.uint8)
+        d[f"size_{nm}"] = np.int64(lm.bytesize(bo))
+    d["getstate"] = np.frombuffer(bytes(lm.__getstate__()), dtype=np.uint8)
+    d["pyhash"] = np.int64(hash(lm))
+    # a batch: C1-like signatures -> records
+    rs = np.random.RandomState(5)
+    sig = rs.randint(0, 2 ** 32, size=(16, 128), dtype=np.uint64)
+    recs = []
+    for row in sig:
+        l = LeanMinHash(seed=9, hashvalues=row)
+        buf = bytearray(l.bytesize())
+        l.serialize(buf)
+        recs.append(np.frombuffer(bytes(buf), dtype=np.uint8))
+    d["batch_sig"] = sig.astype(np.uint32)
+    d["batch_recs"] = np.stack(recs)
+    np.savez_compressed(os.path.join(OUT, "lean.npz"), **d)
+
+
+def gen_wmh():
+    d = {}
+    for dim, ss, seed, nvec, tag in [(64, 16, 1, 24, "small"), (4096, 128, 1, 3, "c4"), (5, 8, 3, 6, "tiny")]:
+        g = WeightedMinHashGenerator(dim, ss, seed)
+        rs = np.random.RandomState(4)
+        v = rs.uniform(0, 10, (nvec, dim)).astype(np.float32)
+        v[:, ::7] = 0
+        if tag == "small":
+            v[1] = np.floor(v[1])            # integer frequencies incl. extra zeros
+            v[2, 2:] = 0                     # single non-zero (col 1)
+            v[3] *= 1e-6                     # tiny weights -> negative logs
+            v[4] *= 1e6
+        out = np.stack([g.minhash(x).hashvalues for x in v]).astype(np.int64)
+        d[f"{tag}_v"] = v
+        d[f"{tag}_out"] = out
+        d[f"{tag}_cfg"] = np.array([dim, ss, seed], dtype=np.int64)
+        if tag != "c4":
+            d[f"{tag}_rs"], d[f"{tag}_ln_cs"], d[f"{tag}_betas"] = g.rs, g.ln_cs, g.betas
+        else:  # params are 6 MB; pin them by a few samples + sums
+            d["c4_rs_head"], d["c4_ln_cs_head"], d["c4_betas_head"] = g.rs[:2, :64], g.ln_cs[:2, :64], g.betas[:2, :64]
+            d["c4_sums"] = np.array([g.rs.astype(np.float64).sum(), g.ln_cs.astype(np.float64).sum(),
+                                     g.betas.astype(np.float64).sum()])
+    np.savez_compressed(os.path.join(OUT, "wmh.npz"), **d)
+
+
+def gen_lsh():
+    d = {}
+    rows = []
+    for thr, k, w in [(0.5, 128, (0.5, 0.5)), (0.8, 128, (0.5, 0.5)), (0.9, 128, (0.5, 0.5)),
+                      (0.8, 256, (0.5, 0.5)), (0.8, 128, (0.2, 0.8)), (0.5, 16, (0.5, 0.5)), (0.5, 32, (0.5, 0.5))]:
+        l = MinHashLSH(threshold=thr, num_perm=k, weights=w)
+        rows.append([thr, k, w[0], w[1], l.b, l.r])
+    d["params"] = np.array(rows, dtype=np.float64)
+    # band keys of a few signatures (lsh.py:344, :537-538)
+    rs = np.random.RandomState(21)
+    docs = [rs.randint(0, 2 ** 32, size=rs.randint(20, 80), dtype=np.uint64) for _ in range(300)]
+    # plant near-duplicates so buckets are non-trivial
+    for i in range(0, 300, 3):
+        src = docs[i].copy()
+        nres = max(1, len(src) // 12)
+        src[rs.choice(len(src), nres, replace=False)] = rs.randint(0, 2 ** 32, size=nres, dtype=np.uint64)
+        docs[i + 1] = src
+        docs[i + 2] = docs[i].copy()     # exact duplicate
+    ms = MinHash.bulk([[int(t) for t in doc] for doc in docs], num_perm=128, seed=1, hashfunc=ident)
+    sig = np.stack([m.hashvalues for m in ms])
+    d["sig"] = sig.astype(np.uint32)
+    lsh = MinHashLSH(threshold=0.8, num_perm=128)
+    d["b_r"] = np.array([lsh.b, lsh.r], dtype=np.int64)
+    for i, m in enumerate(ms):
+        lsh.insert(i, m)
+    keys0 = lsh.keys[0]
+    d["keys_doc0"] = np.frombuffer(b"".join(keys0), dtype=np.uint8).reshape(lsh.b, 8 * lsh.r)
+    res, ptr = [], [0]
+    for m in ms:
+        r = sorted(lsh.query(m))
+        res.extend(r)
+        ptr.append(len(res))
+    d["query_idx"] = np.array(res, dtype=np.int64)
+    d["query_ptr"] = np.array(ptr, dtype=np.int64)
+    counts = lsh.get_counts()
+    d["bucket_counts_sorted"] = np.array(sorted(c for t in counts for c in t.values()), dtype=np.int64)
+    # the reference's pinned candidate set (test/test_lsh.py:109-125): {0, 1}
+    l2 = MinHashLSH(threshold=0.5, num_perm=32)
+    mh = []
+    for toks in ([b"a", b"b", b"c"], [b"a", b"b", b"d"], [b"x", b"y", b"z"]):
+        m = MinHash(num_perm=32)
+        for t in toks:
+            m.update(t)
+        mh.append(m)
+    for i, m in enumerate(mh):
+        l2.insert(i, m)
+    d["abc_sig"] = np.stack([m.hashvalues for m in mh])
+    d["abc_query0"] = np.array(sorted(l2.query(mh[0])), dtype=np.int64)
+    d["abc_b_r"] = np.array([l2.b, l2.r], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "lsh.npz"), **d)
+
+
+if __name__ == "__main__":
+    print("reference:", datasketch.__file__)
+    gen_minhash()
+    gen_lean()
+    gen_wmh()
+    gen_lsh()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
