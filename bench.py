@@ -1,0 +1,365 @@
+"""bench.py -- MinHash signatures/sec on the BASELINE.json workload (configs[1]:
+1M docs x 256 tokens, num_perm=128 bulk signature build), N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's numpy CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic token hashes.
+  value  : whole-job signatures/s with inputs already resident in HBM (CUDA events on the
+           launch stream, max over ranks).  Inputs (1 GB/GPU) are larger than L2.
+  e2e    : same metric through the host-buffer C-ABI call (dsk_minhash_bulk_host) with pinned
+           HOST buffers: H2D of tokens+offsets and D2H of the signatures inside the timed region.
+  roofline: algorithmic bytes (4T+4K per document) / kernel time vs the
+           measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline: the oracle port of the reference's numpy path on all host cores, bounded sample.
+Scaling is weak (each rank builds its own 1M-document shard; documents shard embarrassingly,
+no data-path collective); the optional NCCL all-gather of the signature matrix is timed
+separately and reported under "allgather".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "minhash_signatures_per_sec"
+UNIT = "signatures/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=1_000_000)
+    ap.add_argument("--tokens", type=int, default=256)
+    ap.add_argument("--num-perm", type=int, default=128)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "two_phase", "direct", "exact"])
+    ap.add_argument("--cpu-sample-docs", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------
+def make_tokens(n_docs: int, t: int, seed: int, out: np.ndarray) -> None:
+    """Uniform 32-bit token hashes (i.i.d.), filled chunk-wise into `out`."""
+    rng = np.random.default_rng(seed)
+    flat = out.reshape(-1)
+    step = 1 << 24
+    for i in range(0, flat.size, step):
+        j = min(i + step, flat.size)
+        flat[i:j] = rng.integers(0, 1 << 32, size=j - i, dtype=np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of datasketch's numpy path, all host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    tok, t, k, seed = args
+    from oracle import oracle_np as o
+    off = np.arange(tok.shape[0] + 1, dtype=np.int64) * t
+    sig = o.bulk_signatures_csr(tok.reshape(-1), off, k, seed)
+    return int(sig[:, 0].sum() & 0xFFFF)
+
+
+def cpu_reference_rate(n_docs: int, t: int, k: int, cores: int, repeats: int = 1):
+    """signatures/s of MinHash.bulk's numpy arithmetic (oracle/oracle_np.py) over `cores` processes."""
+    import multiprocessing as mp
+    tok = np.empty((n_docs, t), dtype=np.uint32)
+    make_tokens(n_docs, t, 99, tok)
+    shards = [s for s in np.array_split(tok, cores) if len(s)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(shards)) as pool:
+        pool.map(_cpu_worker, [(s[:8], t, k, 1) for s in shards])  # warm the workers
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(s, t, k, 1) for s in shards])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_docs / best, best
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0: float, t1: float):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, cmax = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = max(mx, cmax)
+            if t0 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for nm, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its numpy uint64
+    arithmetic, restated in oracle/oracle_np.py because /root/reference is absent on the GPU box),
+    on all host cores; each step = a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample_docs or min(args.docs, 2500 * cores)
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, dt = cpu_reference_rate(sample, args.tokens, args.num_perm, cores)
+        if i >= args.warmup:
+            rates.append((r, dt))
+    val = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([dt for _, dt in rates]) * 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: %d docs x %d tokens, num_perm=%d bulk signature build"
+                               % (args.docs, args.tokens, args.num_perm),
+                   "sample_docs_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d docs x %d tokens per step, numpy uint64 path over %d processes"
+                                   % (sample, args.tokens, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import datasketch_b200 as dsk
+    from datasketch_b200 import _native as nv
+    from datasketch_b200.minhash import _make_permutations
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n, t, k = args.docs, args.tokens, args.num_perm
+
+    # ---- CPU baseline on the same box (rank 0, N=1 only), before CUDA is initialised (fork) --------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample_docs or min(n, 2500 * cores)
+        rate, dt = cpu_reference_rate(sample, t, k, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d docs x %d tokens once (%.1f s wall), numpy uint64 path of datasketch over %d processes"
+                         % (sample, t, dt, cores)}
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    perms = _make_permutations(k, 1)
+
+    # ---- synthetic inputs: pinned host copy (for e2e) and resident device copy (for value) ----
+    h_tok_t = torch.empty((n, t), dtype=torch.int32, pin_memory=True)
+    h_tok = h_tok_t.numpy().view(np.uint32)
+    make_tokens(n, t, 1000 + rank, h_tok)
+    h_off_t = torch.arange(0, (n + 1) * t, t, dtype=torch.int64).pin_memory()
+    h_out_t = torch.empty((n, k), dtype=torch.int32, pin_memory=True)
+    d_tok = h_tok_t.to(dev, non_blocking=True)
+    d_off = h_off_t.to(dev, non_blocking=True)
+    d_out = torch.empty((n, k), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        dsk.engine.bulk_signatures_device(d_tok, d_off, n * t, perms, d_out=d_out, kernel=args.kernel,
+                                          stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- value: device-resident, CUDA events ----------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = n * world / (ms_step * 1e-3)
+
+    # parity spot-check on the benchmark's own output (oracle = checker only)
+    if rank == 0:
+        from oracle import oracle_clib as oc
+        idx = np.arange(0, n, max(1, n // 64))[:64]
+        got = d_out[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.uint32)
+        sub = np.ascontiguousarray(h_tok[idx]).reshape(-1)
+        want = oc.minhash_bulk_u32tok(sub, np.arange(len(idx) + 1, dtype=np.int64) * t, perms)
+        if not np.array_equal(got, want):
+            raise SystemExit("bench: GPU signatures differ from the oracle -- number is invalid")
+
+    # ---- e2e: pinned host buffers through the host C-ABI ------------------------------------------
+    e2e = None
+    e2e_launches = 0
+    if not args.no_e2e:
+        h_out = h_out_t.numpy().view(np.uint32)
+        h_off = h_off_t.numpy()
+
+        def step_host():
+            dsk.engine.bulk_signatures(h_tok.reshape(-1), h_off, perms, kernel=args.kernel, device=local, out=h_out)
+
+        for _ in range(max(2, min(args.warmup, 3))):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": n * world * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_tok.nbytes + h_off.nbytes) * world,
+               "d2h_bytes_per_step": int(h_out.nbytes) * world, "ms_per_step": dt / args.steps * 1e3}
+        if rank == 0 and not np.array_equal(h_out[idx], want):
+            raise SystemExit("bench: host-path signatures differ from the oracle -- number is invalid")
+        slices = max(-(-n // (128 << 10)), -(-(n * t) // (16 << 20)))
+        e2e_launches = slices * args.steps
+
+    # ---- optional: NCCL all-gather of the signature matrix (assembly for LSH bucketing) -----------
+    allgather = None
+    if world > 1:
+        full = torch.empty((world * n, k), dtype=torch.int32, device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(full, d_out)
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+            dist.all_gather_into_tensor(full, d_out)
+        ev1.record(stream)
+        barrier()
+        tt = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_g = float(tt.item()) / args.steps
+        allgather = {"value": n * world / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                     "gathered_bytes_per_gpu": int(full.numel() * 4)}
+
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = (4 * t + 4 * k) * n  # per launch, per GPU
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        h = nv.perm_handle(perms, local)
+        kern = args.kernel if args.kernel != "auto" else ("two_phase" if h.n_unsafe == 0 else "exact")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 (mod 2^64 wrap, mod 2^61-1) on u32 lanes", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d docs x %d tokens, num_perm=%d bulk signature build per GPU"
+                                   % (n, t, k),
+                       "kernel": "minhash_bulk_kernel<%s>" % kern, "l2": "inputs (%.2f GB/GPU) larger than L2"
+                                   % (h_tok.nbytes / 1e9), "parallelism": "documents sharded x%d, no collective" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "binding roof is the integer pipe (T*K evaluations/doc), see DESIGN.md"},
+            "e2e": e2e, "gpu_launches": args.steps + e2e_launches, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if allgather is not None:
+            line["allgather"] = allgather
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

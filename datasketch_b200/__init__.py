@@ -1,0 +1,17 @@
+"""datasketch_b200 -- a Blackwell (B200, sm_100a) MinHash / LSH signature engine that keeps
+the API surface of ekzhu/datasketch for the bulk-signature / LSH hot path.
+
+Importing the package loads ``libdsk_b200.so`` (hand-written CUDA behind a C-ABI,
+``include/dsk.h``).  There is no CPU fallback: a missing library fails the import,
+a missing GPU raises RuntimeError on the first compute call.
+"""
+from . import _native
+
+_native.load()  # fail loudly if the CUDA library is absent
+
+from .hashfunc import sha1_hash32, sha1_hash64  # noqa: E402
+from .minhash import MinHash  # noqa: E402
+from . import engine  # noqa: E402
+
+__version__ = "0.1.0"
+__all__ = ["MinHash", "sha1_hash32", "sha1_hash64", "engine"]

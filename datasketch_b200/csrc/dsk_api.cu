@@ -1,0 +1,464 @@
+// dsk_api.cu -- the C-ABI (include/dsk.h): argument validation, permutation analysis,
+// kernel selection, and the pipelined host-buffer entry point.
+#include <mutex>
+#include <new>
+#include <string.h>
+#include <vector>
+
+#include "dsk_common.cuh"
+
+namespace dsk {
+
+// ---- error plumbing -----------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return DSK_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return DSK_ERR_NOMEM;
+    return DSK_ERR_CUDA;
+}
+
+// ---- per-device info cache ---------------------------------------------------------------
+struct DevInfo {
+    bool known = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+};
+static DevInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static int get_dev(int device, DevInfo **out) {
+    if (device < 0 || device >= 64) {
+        set_error("device index %d out of range", device);
+        return DSK_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DevInfo &d = g_dev[device];
+    if (!d.known) {
+        int n = 0;
+        DSK_CUDA(cudaGetDeviceCount(&n));
+        if (device >= n) {
+            set_error("CUDA device %d not present (%d devices); this engine has no CPU fallback", device, n);
+            return DSK_ERR_NO_DEVICE;
+        }
+        cudaDeviceProp p;
+        DSK_CUDA(cudaGetDeviceProperties(&p, device));
+        d.sm_count = p.multiProcessorCount;
+        d.cc_major = p.major;
+        d.cc_minor = p.minor;
+        d.total_mem = p.totalGlobalMem;
+        d.known = true;
+    }
+    *out = &d;
+    return DSK_OK;
+}
+
+// ---- permutation analysis -------------------------------------------------------------------
+// inverse of an odd 64-bit integer modulo 2^64 (Newton iteration doubles the valid bits)
+static uint64_t inv_odd_u64(uint64_t a) {
+    uint64_t x = a;  // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+
+// Is there a token value h in [0, 2^32) with ((a*h + b) mod 2^64) in the set where
+// `% (2^61-1)` takes its conditional subtract, i.e. (x & p) + (x >> 61) >= p ?
+// That set has 36 elements: top3 = j in 0..7 and low61 in [p - j, 2^61 - 1].
+static bool perm_unsafe_u32(uint64_t a, uint64_t b) {
+    const uint64_t p = (1ull << 61) - 1;
+    for (uint64_t j = 0; j < 8; ++j) {
+        for (uint64_t lo = p - j; lo <= p; ++lo) {
+            const uint64_t x = (j << 61) | lo;
+            const uint64_t target = x - b;  // a*h == target (mod 2^64)
+            if (a == 0) {
+                if (target == 0) return true;
+                continue;
+            }
+            const int e = __builtin_ctzll(a);
+            if (e > 0 && (target & ((1ull << e) - 1)) != 0) continue;
+            const int nb = 64 - e;  // h is determined modulo 2^nb
+            if (nb < 32) return true;  // some representative is always < 2^32
+            uint64_t h0 = (target >> e) * inv_odd_u64(a >> e);
+            if (nb < 64) h0 &= (1ull << nb) - 1;
+            if (h0 < (1ull << 32)) return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace dsk
+
+using namespace dsk;
+
+struct dsk_perm {
+    int device = 0;
+    int num_perm = 0;
+    int kpad = 0;
+    int n_unsafe = 0;
+    uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi, each kpad entries
+    std::vector<uint64_t> a, b;
+};
+
+extern "C" {
+
+int dsk_version(void) { return DSK_VERSION; }
+
+const char *dsk_last_error(void) { return g_err; }
+
+int dsk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dsk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+    DevInfo *d;
+    int rc = get_dev(device, &d);
+    if (rc) return rc;
+    if (sm_count) *sm_count = d->sm_count;
+    if (cc_major) *cc_major = d->cc_major;
+    if (cc_minor) *cc_minor = d->cc_minor;
+    if (total_mem) *total_mem = d->total_mem;
+    return DSK_OK;
+}
+
+int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int device, dsk_perm **out) {
+    if (!h_a || !h_b || !out || num_perm <= 0) {
+        set_error("dsk_perm_create: bad arguments (num_perm=%d)", num_perm);
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *d;
+    int rc = get_dev(device, &d);
+    if (rc) return rc;
+    if (d->cc_major < 10) {
+        set_error("device %d is sm_%d%d; this library ships sm_100a code only", device, d->cc_major, d->cc_minor);
+        return DSK_ERR_NO_DEVICE;
+    }
+    dsk_perm *p = new (std::nothrow) dsk_perm();
+    if (!p) return DSK_ERR_NOMEM;
+    p->device = device;
+    p->num_perm = num_perm;
+    p->kpad = (num_perm + 255) / 256 * 256;
+    p->a.assign(h_a, h_a + num_perm);
+    p->b.assign(h_b, h_b + num_perm);
+    std::vector<uint32_t> tab((size_t)4 * p->kpad, 0u);
+    for (int i = 0; i < num_perm; ++i) {
+        tab[i] = (uint32_t)h_a[i];
+        tab[p->kpad + i] = (uint32_t)(h_a[i] >> 32);
+        tab[2 * p->kpad + i] = (uint32_t)h_b[i];
+        tab[3 * p->kpad + i] = (uint32_t)(h_b[i] >> 32);
+        if (perm_unsafe_u32(h_a[i], h_b[i])) p->n_unsafe++;
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_tab, tab.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        if (p->d_tab) cudaFree(p->d_tab);
+        delete p;
+        return cuda_fail(e, "dsk_perm_create upload");
+    }
+    *out = p;
+    return DSK_OK;
+}
+
+int dsk_perm_analyze(const uint64_t *h_a, const uint64_t *h_b, int num_perm, uint8_t *out_unsafe) {
+    int n = 0;
+    for (int i = 0; i < num_perm; ++i) {
+        const bool u = perm_unsafe_u32(h_a[i], h_b[i]);
+        if (out_unsafe) out_unsafe[i] = u ? 1 : 0;
+        n += u;
+    }
+    return n;
+}
+
+int dsk_perm_info(const dsk_perm *p, int *num_perm, int *n_unsafe, int *device) {
+    if (!p) {
+        set_error("dsk_perm_info: null handle");
+        return DSK_ERR_INVALID;
+    }
+    if (num_perm) *num_perm = p->num_perm;
+    if (n_unsafe) *n_unsafe = p->n_unsafe;
+    if (device) *device = p->device;
+    return DSK_OK;
+}
+
+void dsk_perm_destroy(dsk_perm *p) {
+    if (!p) return;
+    if (p->d_tab) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(p->device);
+        cudaFree(p->d_tab);
+        cudaSetDevice(prev);
+    }
+    delete p;
+}
+
+static int pick_mode(const dsk_perm *perm, int token_is_u64, int flags, int *mode) {
+    const bool fast_ok = !token_is_u64 && perm->n_unsafe == 0;
+    switch (flags) {
+        case DSK_KERNEL_AUTO: *mode = fast_ok ? MODE_TWO_PHASE : MODE_EXACT; return DSK_OK;
+        case DSK_KERNEL_TWO_PHASE:
+        case DSK_KERNEL_DIRECT:
+            if (!fast_ok) {
+                set_error("fast kernels are not exact here (token_is_u64=%d, unsafe permutations=%d); use DSK_KERNEL_EXACT/AUTO",
+                          token_is_u64, perm->n_unsafe);
+                return DSK_ERR_INVALID;
+            }
+            *mode = (flags == DSK_KERNEL_TWO_PHASE) ? MODE_TWO_PHASE : MODE_DIRECT;
+            return DSK_OK;
+        case DSK_KERNEL_EXACT: *mode = MODE_EXACT; return DSK_OK;
+        default: set_error("unknown kernel flag %d", flags); return DSK_ERR_INVALID;
+    }
+}
+
+int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u64, const int64_t *d_offsets,
+                     int64_t n_docs, int64_t n_tokens, const void *d_init, int64_t init_stride, int init_is_u64,
+                     void *d_out, int out_is_u64, int flags, void *stream) {
+    if (!perm || !d_offsets || !d_out || n_docs < 0 || n_tokens < 0 || (n_tokens > 0 && !d_tokens)) {
+        set_error("dsk_minhash_bulk: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (n_docs == 0) return DSK_OK;
+    if (((uintptr_t)d_tokens & 15) != 0) {
+        set_error("dsk_minhash_bulk: d_tokens must be 16-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    if (((uintptr_t)d_out & 15) != 0 || ((uintptr_t)d_offsets & 7) != 0) {
+        set_error("dsk_minhash_bulk: d_out must be 16-byte aligned and d_offsets 8-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    int mode;
+    int rc = pick_mode(perm, token_is_u64, flags, &mode);
+    if (rc) return rc;
+    DevInfo *dev;
+    rc = get_dev(perm->device, &dev);
+    if (rc) return rc;
+    BulkParams prm;
+    prm.tokens = d_tokens;
+    prm.offsets = d_offsets;
+    prm.n_docs = n_docs;
+    prm.n_tokens = n_tokens;
+    prm.a_lo = perm->d_tab;
+    prm.a_hi = perm->d_tab + perm->kpad;
+    prm.b_lo = perm->d_tab + 2 * perm->kpad;
+    prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.k = perm->num_perm;
+    prm.init = d_init;
+    prm.init_stride = init_stride;
+    prm.init_is_u64 = init_is_u64;
+    prm.out = d_out;
+    prm.out_is_u64 = out_is_u64;
+    DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_sig_merge_min(const uint32_t *d_x, const uint32_t *d_y, int64_t n_elems, uint32_t *d_out, void *stream) {
+    if (n_elems < 0 || (n_elems > 0 && (!d_x || !d_y || !d_out))) {
+        set_error("dsk_sig_merge_min: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    int device = 0;
+    DSK_CUDA(cudaGetDevice(&device));
+    DevInfo *dev;
+    int rc = get_dev(device, &dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_sig_merge_min(d_x, d_y, n_elems, d_out, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+// ---- host-buffer pipeline --------------------------------------------------------------------
+namespace {
+constexpr int kSlots = 3;
+struct HostPipe {
+    int device = -1;
+    cudaStream_t stream[kSlots] = {};
+    void *d_tok[kSlots] = {};
+    int64_t *d_off[kSlots] = {};
+    void *d_out[kSlots] = {};
+    void *d_init[kSlots] = {};
+    int64_t *h_off[kSlots] = {};  // pinned staging for rebased offsets
+    size_t cap_tok = 0, cap_docs = 0, cap_out = 0, cap_init = 0;
+};
+HostPipe g_pipe[64];
+std::mutex g_pipe_mu;
+
+int pipe_reserve(HostPipe &hp, int device, size_t tok_bytes, size_t docs, size_t out_bytes, size_t init_bytes) {
+    if (hp.device < 0) {
+        for (int i = 0; i < kSlots; ++i) DSK_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+        hp.device = device;
+    }
+    if (tok_bytes > hp.cap_tok) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (hp.d_tok[i]) cudaFree(hp.d_tok[i]);
+            hp.d_tok[i] = nullptr;
+            DSK_CUDA(cudaMalloc(&hp.d_tok[i], tok_bytes + 64));
+        }
+        hp.cap_tok = tok_bytes;
+    }
+    if (docs > hp.cap_docs) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (hp.d_off[i]) cudaFree(hp.d_off[i]);
+            if (hp.h_off[i]) cudaFreeHost(hp.h_off[i]);
+            hp.d_off[i] = nullptr;
+            hp.h_off[i] = nullptr;
+            DSK_CUDA(cudaMalloc(&hp.d_off[i], (docs + 1) * sizeof(int64_t)));
+            DSK_CUDA(cudaMallocHost(&hp.h_off[i], (docs + 1) * sizeof(int64_t)));
+        }
+        hp.cap_docs = docs;
+    }
+    if (out_bytes > hp.cap_out) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (hp.d_out[i]) cudaFree(hp.d_out[i]);
+            hp.d_out[i] = nullptr;
+            DSK_CUDA(cudaMalloc(&hp.d_out[i], out_bytes + 64));
+        }
+        hp.cap_out = out_bytes;
+    }
+    if (init_bytes > hp.cap_init) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (hp.d_init[i]) cudaFree(hp.d_init[i]);
+            hp.d_init[i] = nullptr;
+            DSK_CUDA(cudaMalloc(&hp.d_init[i], init_bytes + 64));
+        }
+        hp.cap_init = init_bytes;
+    }
+    return DSK_OK;
+}
+}  // namespace
+
+int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_is_u64, const int64_t *h_offsets,
+                          int64_t n_docs, const void *h_init, int64_t init_stride, int init_is_u64, void *h_out,
+                          int out_is_u64, int flags) {
+    if (!perm || !h_offsets || !h_out || n_docs < 0) {
+        set_error("dsk_minhash_bulk_host: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (n_docs == 0) return DSK_OK;
+    const int64_t n_tokens = h_offsets[n_docs] - h_offsets[0];
+    if (n_tokens < 0 || (n_tokens > 0 && !h_tokens)) {
+        set_error("dsk_minhash_bulk_host: bad offsets / tokens");
+        return DSK_ERR_INVALID;
+    }
+    int mode;
+    int rc = pick_mode(perm, token_is_u64, flags, &mode);
+    if (rc) return rc;
+    DevInfo *dev;
+    rc = get_dev(perm->device, &dev);
+    if (rc) return rc;
+
+    const size_t tsz = token_is_u64 ? 8 : 4, osz = out_is_u64 ? 8 : 4;
+    const int K = perm->num_perm;
+    // slice limits: ~16 Mi tokens and 128 Ki documents per slice keep each copy in the MB range
+    const int64_t max_tok = 16ll << 20, max_docs = 128ll << 10;
+
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    DSK_CUDA(cudaSetDevice(perm->device));
+    HostPipe &hp = g_pipe[perm->device];
+
+    // first pass: slice boundaries (a single document larger than max_tok gets its own slice)
+    std::vector<int64_t> cut;
+    cut.push_back(0);
+    int64_t biggest_tok = 0, biggest_docs = 0;
+    {
+        int64_t d0 = 0;
+        while (d0 < n_docs) {
+            int64_t d1 = d0;
+            const int64_t t0 = h_offsets[d0];
+            while (d1 < n_docs && d1 - d0 < max_docs && (h_offsets[d1 + 1] - t0 <= max_tok || d1 == d0)) ++d1;
+            if (h_offsets[d1] < h_offsets[d0]) {
+                cudaSetDevice(prev);
+                set_error("dsk_minhash_bulk_host: offsets must be non-decreasing");
+                return DSK_ERR_INVALID;
+            }
+            biggest_tok = biggest_tok > h_offsets[d1] - t0 ? biggest_tok : h_offsets[d1] - t0;
+            biggest_docs = biggest_docs > d1 - d0 ? biggest_docs : d1 - d0;
+            cut.push_back(d1);
+            d0 = d1;
+        }
+    }
+    const size_t isz = init_is_u64 ? 8 : 4;
+    const size_t init_rows = !h_init ? 0 : (init_stride == 0 ? 1 : (size_t)biggest_docs);
+    if (h_init && init_stride != 0 && init_stride < K) {
+        cudaSetDevice(prev);
+        set_error("dsk_minhash_bulk_host: init_stride must be 0 or >= num_perm");
+        return DSK_ERR_INVALID;
+    }
+    rc = pipe_reserve(hp, perm->device, (size_t)biggest_tok * tsz, (size_t)biggest_docs, (size_t)biggest_docs * K * osz,
+                      init_rows * (size_t)(init_stride ? init_stride : K) * isz);
+    if (rc) {
+        cudaSetDevice(prev);
+        return rc;
+    }
+
+    BulkParams prm;
+    prm.a_lo = perm->d_tab;
+    prm.a_hi = perm->d_tab + perm->kpad;
+    prm.b_lo = perm->d_tab + 2 * perm->kpad;
+    prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.k = K;
+    prm.init = nullptr;
+    prm.init_stride = init_stride;
+    prm.init_is_u64 = init_is_u64;
+    prm.out_is_u64 = out_is_u64;
+
+    cudaError_t e = cudaSuccess;
+    for (size_t s = 0; s + 1 < cut.size() && e == cudaSuccess; ++s) {
+        const int slot = (int)(s % kSlots);
+        const int64_t d0 = cut[s], d1 = cut[s + 1], nd = d1 - d0;
+        const int64_t t0 = h_offsets[d0], nt = h_offsets[d1] - t0;
+        cudaStream_t st = hp.stream[slot];
+        // the pinned offsets staging buffer of this slot is reused: wait for its previous slice
+        if (s >= (size_t)kSlots) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) break;
+        for (int64_t i = 0; i <= nd; ++i) hp.h_off[slot][i] = h_offsets[d0 + i] - t0;
+        if (nt > 0)
+            e = cudaMemcpyAsync(hp.d_tok[slot], (const char *)h_tokens + (size_t)t0 * tsz, (size_t)nt * tsz,
+                                cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(hp.d_off[slot], hp.h_off[slot], (size_t)(nd + 1) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && h_init) {
+            const size_t rows = init_stride == 0 ? 1 : (size_t)nd;
+            const size_t row_elems = (size_t)(init_stride ? init_stride : K);
+            const char *src = (const char *)h_init + (init_stride == 0 ? 0 : (size_t)d0 * row_elems * isz);
+            e = cudaMemcpyAsync(hp.d_init[slot], src, rows * row_elems * isz, cudaMemcpyHostToDevice, st);
+            prm.init = hp.d_init[slot];
+        }
+        if (e != cudaSuccess) break;
+        prm.tokens = hp.d_tok[slot];
+        prm.offsets = hp.d_off[slot];
+        prm.n_docs = nd;
+        prm.n_tokens = nt;
+        prm.out = hp.d_out[slot];
+        e = launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char *)h_out + (size_t)d0 * K * osz, hp.d_out[slot], (size_t)nd * K * osz,
+                                cudaMemcpyDeviceToHost, st);
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        cudaError_t e2 = cudaStreamSynchronize(hp.stream[i]);
+        if (e == cudaSuccess) e = e2;
+    }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "dsk_minhash_bulk_host pipeline");
+    return DSK_OK;
+}
+
+}  // extern "C"

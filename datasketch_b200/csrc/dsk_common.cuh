@@ -1,0 +1,108 @@
+// dsk_common.cuh -- shared device helpers (sm_100a): mbarrier / bulk-copy (TMA) PTX,
+// error plumbing.  No torch, no libraries: plain CUDA runtime + inline PTX.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/dsk.h"
+
+namespace dsk {
+
+// ---- thread-local error string --------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define DSK_CUDA(call)                                            \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return ::dsk::cuda_fail(e__, #call); \
+    } while (0)
+
+// ---- parameters of the bulk signature kernels (minhash_kernels.cu) ----------------------
+struct BulkParams {
+    const void *tokens;         // u32 or u64 token hashes, 16-byte aligned
+    const int64_t *offsets;     // [n_docs + 1] CSR offsets relative to `tokens`
+    int64_t n_docs, n_tokens;
+    const uint32_t *a_lo, *a_hi, *b_lo, *b_hi;  // permutation halves, zero-padded to a multiple of 256
+    int k;                      // num_perm
+    const void *init;           // running signatures to merge, or nullptr
+    int64_t init_stride;        // elements between init rows (0 = broadcast one row)
+    int init_is_u64;
+    void *out;                  // [n_docs, k] u32 or u64
+    int out_is_u64;
+};
+enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
+cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
+cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n, uint32_t *out, int sm_count,
+                                 cudaStream_t s);
+
+// ---- PTX helpers -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// make mbarrier.init visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 1-D bulk async copy global -> shared (TMA engine; SASS: UBLKCP).  dst/src 16-byte
+// aligned, bytes a multiple of 16; completion is signalled as tx-bytes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 1-D bulk async copy shared -> global (SASS: UBLKCP / UTMASTG family), bulk-group completion.
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+
+}  // namespace dsk

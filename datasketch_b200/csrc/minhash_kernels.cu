@@ -1,0 +1,383 @@
+// minhash_kernels.cu -- the permutation-hash-and-min path as hand-written sm_100a CUDA.
+//
+// Replaces datasketch/minhash.py:294-297 (numpy) / :281-291 (CuPy) batched over
+// documents as MinHash.bulk does (:464-522).  See DESIGN.md "Kernel 1".
+//
+// Work decomposition
+//   warp  <-> a contiguous range of documents (token-balanced static partition of the CSR
+//             batch), streamed through a per-warp double-buffered shared-memory ring that
+//             is filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier), 2 KB per chunk.
+//   lane  <-> P consecutive permutations (a_k, b_k live in registers); a 16-token block is
+//             read back from shared memory with four broadcast LDS.128.
+//
+// Arithmetic (bit-exact with numpy's uint64 wrap-then-mod):
+//   x = (a*h + b) mod 2^64;  r = (x mod (2^61-1)) & 0xFFFFFFFF
+//   With p = 2^61-1:  x mod p = (x & p) + (x >> 61), minus p iff that sum >= p.  The
+//   subtract fires for only 36 of the 2^64 values of x; dsk_perm_create proves on the host
+//   (modular inverses) that no 32-bit token can reach them for a given permutation set, and
+//   then   r = lo32(x) + (hi32(x) >> 29)   exactly  (IMAD.WIDE + IMAD + LEA.HI).
+//
+// TWO_PHASE kernel (default): per evaluation only  L' = lo32(a_lo*h + b_lo + 7)  is computed
+//   (one IMAD) and min-reduced with VIMNMX3; since r = L' - (7 - top3(x)) lies in [L'-7, L'],
+//   the true minimum can only come from 16-token blocks whose block-min L' is within 7 of the
+//   document min.  Each lane tracks (min, argmin block, second-smallest block min) and then
+//   re-evaluates just the winning block exactly; if another block is within the window (or
+//   the min is < 7, where L'-7 would wrap) a slow exact pass over candidate blocks runs.
+// DIRECT kernel: the full 3.5-instruction evaluation for every (token, perm).
+// EXACT kernel: true 64-bit `% p` for every evaluation (any permutation, u32 or u64 tokens).
+#include "dsk_common.cuh"
+
+namespace dsk {
+
+constexpr int kWarps = 4;           // warps per CTA
+constexpr int kChunkBytes = 2048;   // bytes per TMA bulk copy / ring slot
+constexpr int kNBuf = 2;            // ring depth per warp
+constexpr int kBlkTok = 16;         // tokens per block (phase-1 tracking granularity)
+constexpr uint64_t kP61 = (1ull << 61) - 1;
+
+// r = lo32(x) + top3(x), valid when the `% p` subtract cannot fire (see header).
+__device__ __forceinline__ uint32_t eval_fast(uint32_t alo, uint32_t ahi, uint64_t b, uint32_t h) {
+    uint64_t x = (uint64_t)alo * h + b;                     // IMAD.WIDE.U32
+    uint32_t xh = (uint32_t)(x >> 32) + ahi * h;            // IMAD
+    return (uint32_t)x + (xh >> 29);                        // LEA.HI
+}
+
+// true ((a*h+b) mod 2^64) % (2^61-1), low 32 bits
+__device__ __forceinline__ uint32_t eval_exact(uint64_t a, uint64_t b, uint64_t h) {
+    uint64_t x = a * h + b;
+    uint64_t s = (x & kP61) + (x >> 61);
+    if (s >= kP61) s -= kP61;
+    return (uint32_t)s;
+}
+
+// first d in [0, n] with off[d] >= v
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t *off, int64_t n, int64_t v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <typename TokT> struct TokLoad;
+template <> struct TokLoad<uint32_t> {
+    // 16 tokens = 4 x LDS.128 (all lanes read the same address: broadcast, 1 wavefront each)
+    static __device__ __forceinline__ void block(const uint32_t *src, uint32_t (&t)[kBlkTok]) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 v = q[i];
+            t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+        }
+    }
+};
+template <> struct TokLoad<uint64_t> {
+    static __device__ __forceinline__ void block(const uint64_t *src, uint64_t (&t)[kBlkTok]) {
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(src);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ulonglong2 v = q[i];
+            t[2 * i] = v.x; t[2 * i + 1] = v.y;
+        }
+    }
+};
+
+template <int P, int MODE, typename TokT>
+__global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkParams prm) {
+    static_assert(MODE == MODE_EXACT || sizeof(TokT) == 4, "fast paths need 32-bit token hashes");
+    constexpr int kBlkBytes = kBlkTok * (int)sizeof(TokT);
+    constexpr int kBlkPerChunk = kChunkBytes / kBlkBytes;
+
+    __shared__ __align__(128) unsigned char s_buf[kWarps][kNBuf][kChunkBytes];
+    __shared__ __align__(16) TokT s_scratch[kWarps][kBlkTok];
+    __shared__ __align__(8) uint64_t s_bar[kWarps][kNBuf];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t nw = (int64_t)gridDim.x * kWarps;
+    const TokT *__restrict__ tokens = static_cast<const TokT *>(prm.tokens);
+    const int64_t *__restrict__ offsets = prm.offsets;
+    const int K = prm.k;
+    const int kl = blockIdx.y * (32 * P) + lane * P;  // first permutation owned by this lane
+
+    // ---- token-balanced static partition of documents over warps -------------------
+    const int64_t n_docs = prm.n_docs, n_tokens = prm.n_tokens;
+    int64_t dlo, dhi;
+    {
+        // n_tokens * gw < 2^63 for any batch that fits in HBM
+        int64_t t0 = (n_tokens / nw) * gw + (n_tokens % nw) * gw / nw;
+        int64_t t1 = (n_tokens / nw) * (gw + 1) + (n_tokens % nw) * (gw + 1) / nw;
+        dlo = (gw == 0) ? 0 : lower_bound_i64(offsets, n_docs, t0);
+        dhi = (gw == nw - 1) ? n_docs : lower_bound_i64(offsets, n_docs, t1);
+    }
+    if (dlo >= dhi) return;
+
+    // ---- permutation parameters -> registers ------------------------------------------
+    uint32_t alo[P], ahi[P], blo[P], bhi[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        alo[j] = __ldg(prm.a_lo + kl + j); ahi[j] = __ldg(prm.a_hi + kl + j);
+        blo[j] = __ldg(prm.b_lo + kl + j); bhi[j] = __ldg(prm.b_hi + kl + j);
+    }
+
+    // ---- per-warp TMA ring --------------------------------------------------------------
+    const int64_t tok_lo = __ldg(offsets + dlo), tok_hi = __ldg(offsets + dhi);
+    const int64_t blk_begin = tok_lo / kBlkTok;
+    const int64_t blk_end = (tok_hi + kBlkTok - 1) / kBlkTok;
+    const int64_t nchunks = (tok_hi > tok_lo) ? (blk_end - blk_begin + kBlkPerChunk - 1) / kBlkPerChunk : 0;
+    const int64_t copy_end_bytes = (n_tokens * (int64_t)sizeof(TokT)) & ~(int64_t)15;  // bulk copies need 16 B granules
+    const int64_t tail_tok = copy_end_bytes / (int64_t)sizeof(TokT);                  // tokens >= this come by plain loads
+
+    uint64_t *bar = s_bar[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kNBuf; ++i) mbar_init(&bar[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    auto issue = [&](int64_t c) {  // lane 0 only
+        const int slot = (int)(c % kNBuf);
+        const int64_t b0 = blk_begin + c * kBlkPerChunk;
+        const int64_t b1 = min(b0 + (int64_t)kBlkPerChunk, blk_end);
+        const int64_t byte_lo = b0 * kBlkBytes;
+        const int64_t byte_hi = min(b1 * kBlkBytes, copy_end_bytes);
+        if (byte_hi > byte_lo) {
+            const uint32_t bytes = (uint32_t)(byte_hi - byte_lo);
+            mbar_arrive_expect_tx(&bar[slot], bytes);
+            bulk_g2s(s_buf[warp][slot], reinterpret_cast<const unsigned char *>(tokens) + byte_lo, bytes, &bar[slot]);
+        } else {
+            mbar_arrive(&bar[slot]);
+        }
+    };
+    if (lane == 0) {
+        for (int64_t c = 0; c < min(nchunks, (int64_t)kNBuf); ++c) issue(c);
+    }
+
+    int64_t cur = 0;     // chunk currently mapped
+    bool ready = false;  // cur has been waited on
+    auto map_chunk = [&](int64_t c) {
+        while (cur < c) {
+            __syncwarp();  // every lane is done reading slot cur % kNBuf
+            if (lane == 0 && cur + kNBuf < nchunks) issue(cur + kNBuf);
+            ++cur;
+            ready = false;
+        }
+        if (!ready) {
+            mbar_wait(&bar[cur % kNBuf], (uint32_t)((cur / kNBuf) & 1));
+            // the last (< 16 B) tokens of the whole array cannot travel by bulk copy
+            const int64_t c0 = (blk_begin + cur * kBlkPerChunk) * kBlkTok;
+            const int64_t i = tail_tok + lane;
+            if (i < n_tokens && i >= c0 && i < c0 + (int64_t)kBlkPerChunk * kBlkTok)
+                reinterpret_cast<TokT *>(s_buf[warp][cur % kNBuf])[i - c0] = tokens[i];
+            __syncwarp();
+            ready = true;
+        }
+    };
+
+    // ---- documents ---------------------------------------------------------------------
+    int64_t start = tok_lo;
+    for (int64_t d = dlo; d < dhi; ++d) {
+        const int64_t end = __ldg(offsets + d + 1);
+
+        uint32_t m[P], m2[P], widx[P];  // TWO_PHASE: min L', 2nd-smallest block min, winning block
+#pragma unroll
+        for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; widx[j] = 0; }
+
+        if (end > start) {
+            const int64_t bfirst = start / kBlkTok, blast = (end - 1) / kBlkTok;
+            for (int64_t blk = bfirst; blk <= blast; ++blk) {
+                map_chunk((blk - blk_begin) / kBlkPerChunk);
+                const int64_t cblk0 = blk_begin + cur * kBlkPerChunk;
+                const TokT *cbuf = reinterpret_cast<const TokT *>(s_buf[warp][cur % kNBuf]);
+                const TokT *src = cbuf + (blk - cblk0) * kBlkTok;
+                const bool partial = (blk * kBlkTok < start) || (blk * kBlkTok + kBlkTok > end);
+                if (partial) {
+                    // boundary block: out-of-document slots are replaced by a duplicate of an
+                    // in-document token (min is idempotent), then the block is handled uniformly
+                    if (lane < kBlkTok) {
+                        int64_t i = blk * kBlkTok + lane;
+                        i = max(start, min(i, end - 1));
+                        s_scratch[warp][lane] = cbuf[i - cblk0 * kBlkTok];
+                    }
+                    __syncwarp();
+                    src = s_scratch[warp];
+                }
+                TokT t[kBlkTok];
+                TokLoad<TokT>::block(src, t);
+                if (partial) __syncwarp();  // scratch may be rewritten by the next block
+
+                if constexpr (MODE == MODE_TWO_PHASE) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint32_t c7 = blo[j] + 7u;
+                        uint32_t bm = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 0; i < kBlkTok; i += 2)
+                            bm = umin3(bm, alo[j] * (uint32_t)t[i] + c7, alo[j] * (uint32_t)t[i + 1] + c7);
+                        const uint32_t om = m[j];
+                        m2[j] = min(m2[j], max(bm, om));
+                        if (bm < om) { m[j] = bm; widx[j] = (uint32_t)blk; }
+                    }
+                } else if constexpr (MODE == MODE_DIRECT) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+#pragma unroll
+                        for (int i = 0; i < kBlkTok; i += 2)
+                            m[j] = umin3(m[j], eval_fast(alo[j], ahi[j], b64, (uint32_t)t[i]),
+                                         eval_fast(alo[j], ahi[j], b64, (uint32_t)t[i + 1]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint64_t a64 = ((uint64_t)ahi[j] << 32) | alo[j];
+                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+#pragma unroll 4
+                        for (int i = 0; i < kBlkTok; ++i) m[j] = min(m[j], eval_exact(a64, b64, (uint64_t)t[i]));
+                    }
+                }
+            }
+        }
+
+        // ---- finalise the document ---------------------------------------------------------
+        uint32_t res[P];
+        if constexpr (MODE == MODE_TWO_PHASE) {
+            unsigned need_slow = 0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                uint32_t r = 0xFFFFFFFFu;
+                if (end > start) {
+                    const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+                    const int64_t base = (int64_t)widx[j] * kBlkTok;
+#pragma unroll 4
+                    for (int i = 0; i < kBlkTok; ++i) {
+                        const int64_t p = max(start, min(base + i, end - 1));
+                        r = min(r, eval_fast(alo[j], ahi[j], b64, (uint32_t)__ldg(tokens + p)));
+                    }
+                    // another block within the +7 window, or L'-7 could wrap: resolve exactly below
+                    if (m[j] < 7u || (m2[j] - m[j]) <= 7u) need_slow |= 1u << j;
+                }
+                res[j] = r;
+            }
+            if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
+                uint32_t rs[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j) rs[j] = 0xFFFFFFFFu;
+                for (int64_t blk = start / kBlkTok; blk <= (end - 1) / kBlkTok; ++blk) {
+                    uint32_t t[kBlkTok];
+#pragma unroll
+                    for (int i = 0; i < kBlkTok; ++i) {
+                        const int64_t p = max(start, min(blk * kBlkTok + i, end - 1));
+                        t[i] = (uint32_t)__ldg(tokens + p);
+                    }
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        if (!((need_slow >> j) & 1u)) continue;
+                        const uint32_t c7 = blo[j] + 7u;
+                        uint32_t bm = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 0; i < kBlkTok; ++i) bm = min(bm, alo[j] * t[i] + c7);
+                        if (m[j] < 7u || (uint64_t)bm <= (uint64_t)m[j] + 7u) {
+                            const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+#pragma unroll 4
+                            for (int i = 0; i < kBlkTok; ++i) rs[j] = min(rs[j], eval_fast(alo[j], ahi[j], b64, t[i]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    if ((need_slow >> j) & 1u) res[j] = rs[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; ++j) res[j] = m[j];
+        }
+
+        // ---- merge with the running state (minhash.py:297) and store ---------------------------
+        if (prm.init != nullptr) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                if (kl + j < K) {
+                    const int64_t e = d * prm.init_stride + kl + j;
+                    if (prm.init_is_u64) {
+                        const uint64_t v = __ldg(static_cast<const uint64_t *>(prm.init) + e);
+                        res[j] = (uint32_t)min((uint64_t)res[j], v);  // res <= 2^32-1 so the min fits
+                    } else {
+                        res[j] = min(res[j], __ldg(static_cast<const uint32_t *>(prm.init) + e));
+                    }
+                }
+            }
+        }
+        if (prm.out_is_u64) {
+            uint64_t *row = static_cast<uint64_t *>(prm.out) + d * (int64_t)K + kl;
+#pragma unroll
+            for (int j = 0; j < P; ++j)
+                if (kl + j < K) row[j] = res[j];
+        } else {
+            uint32_t *row = static_cast<uint32_t *>(prm.out) + d * (int64_t)K + kl;
+            if (P == 4 && (K & 3) == 0) {
+                if (kl < K) *reinterpret_cast<uint4 *>(row) = make_uint4(res[0], res[1], res[2 % P], res[3 % P]);
+            } else if (P == 8 && (K & 7) == 0) {
+                if (kl < K) {
+                    reinterpret_cast<uint4 *>(row)[0] = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
+                    reinterpret_cast<uint4 *>(row)[1] = make_uint4(res[4 % P], res[5 % P], res[6 % P], res[7 % P]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    if (kl + j < K) row[j] = res[j];
+            }
+        }
+        start = end;
+    }
+}
+
+// ---- element-wise min of signature matrices (MinHash.merge / union) --------------------
+__global__ void sig_merge_min_kernel(const uint32_t *__restrict__ x, const uint32_t *__restrict__ y,
+                                     int64_t n, uint32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = min(x[i], y[i]);
+}
+
+// ---- launchers --------------------------------------------------------------------------------
+template <int P, int MODE, typename TokT>
+static cudaError_t launch_bulk(const BulkParams &prm, int sm_count, cudaStream_t s) {
+    const int slices = (prm.k + 32 * P - 1) / (32 * P);
+    int64_t gx = (prm.n_docs + kWarps - 1) / kWarps;
+    const int64_t gmax = (int64_t)sm_count * 4;
+    if (gx > gmax) gx = gmax;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)slices);
+    minhash_bulk_kernel<P, MODE, TokT><<<grid, kWarps * 32, 0, s>>>(prm);
+    return cudaGetLastError();
+}
+
+template <int MODE, typename TokT>
+static cudaError_t launch_bulk_p(const BulkParams &prm, int sm_count, cudaStream_t s) {
+    if (prm.k <= 32) return launch_bulk<1, MODE, TokT>(prm, sm_count, s);
+    if (prm.k <= 64) return launch_bulk<2, MODE, TokT>(prm, sm_count, s);
+    if (prm.k <= 128) return launch_bulk<4, MODE, TokT>(prm, sm_count, s);
+    return launch_bulk<8, MODE, TokT>(prm, sm_count, s);
+}
+
+cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s) {
+    if (token_is_u64) return launch_bulk_p<MODE_EXACT, uint64_t>(prm, sm_count, s);
+    switch (mode) {
+        case MODE_TWO_PHASE: return launch_bulk_p<MODE_TWO_PHASE, uint32_t>(prm, sm_count, s);
+        case MODE_DIRECT: return launch_bulk_p<MODE_DIRECT, uint32_t>(prm, sm_count, s);
+        default: return launch_bulk_p<MODE_EXACT, uint32_t>(prm, sm_count, s);
+    }
+}
+
+cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n, uint32_t *out, int sm_count,
+                                 cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    sig_merge_min_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, y, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace dsk

@@ -1,0 +1,121 @@
+"""Batch-native entry points over the C-ABI (the calls MinHash / MinHashLSH make).
+
+Host code stays Python; every function here ends in one call into
+libdsk_b200.so.  torch is used only to own device buffers and streams.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nv
+
+KERNELS = {"auto": nv.KERNEL_AUTO, "two_phase": nv.KERNEL_TWO_PHASE, "direct": nv.KERNEL_DIRECT,
+           "exact": nv.KERNEL_EXACT}
+
+
+def _as_tokens(tokens) -> Tuple[np.ndarray, int]:
+    """Contiguous u32 (32-bit hash contract, minhash.py:69-70) or u64 token array."""
+    t = np.asarray(tokens)
+    if t.dtype == np.uint32:
+        return np.ascontiguousarray(t), 0
+    if t.dtype == np.uint64:
+        return np.ascontiguousarray(t), 1
+    if t.dtype.kind in "iu":
+        if t.size and (t.min() < 0):
+            raise OverflowError("token hash values must be non-negative")  # numpy raises the same on uint64 cast
+        if t.size == 0 or int(t.max()) < (1 << 32):
+            return np.ascontiguousarray(t.astype(np.uint32)), 0
+        return np.ascontiguousarray(t.astype(np.uint64)), 1
+    raise TypeError("token hashes must be an integer array, got dtype %s" % t.dtype)
+
+
+def pack_docs(docs: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    """List of integer-hash lists -> (tokens, offsets) CSR.  u32 storage when every hash fits 32 bits."""
+    lens = np.fromiter((len(d) for d in docs), dtype=np.int64, count=len(docs))
+    offsets = np.zeros(len(docs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    flat = [h for d in docs for h in d]
+    if not flat:
+        return np.zeros(0, dtype=np.uint32), offsets
+    try:
+        tok = np.array(flat, dtype=np.uint64)  # same cast (and OverflowError on negatives) as minhash.py:294
+    except OverflowError:
+        raise
+    if int(tok.max()) < (1 << 32):
+        tok = tok.astype(np.uint32)
+    return tok, offsets
+
+
+def bulk_signatures(tokens, offsets, permutations: np.ndarray, init: Optional[np.ndarray] = None,
+                    out_u64: bool = False, kernel: str = "auto", device: int = 0,
+                    out: Optional[np.ndarray] = None) -> np.ndarray:
+    """HOST arrays in, HOST [N, K] signature matrix out (u32, or u64 = the reference's dtype).
+
+    One call to ``dsk_minhash_bulk_host``: slices of documents are pipelined
+    H2D -> kernel -> D2H on internal streams.  ``init`` is ``None`` (empty
+    state), one row (broadcast) or an [N, K] matrix of running signatures.
+    """
+    nv.require_device(device)
+    tok, is64 = _as_tokens(tokens)
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    if off.ndim != 1 or off.size < 1:
+        raise ValueError("offsets must be a 1-D array of length n_docs + 1")
+    n = off.size - 1
+    if n and (int(off[-1]) - int(off[0]) > tok.size or int(off[0]) < 0):
+        raise ValueError("offsets exceed the token array")
+    h = nv.perm_handle(permutations, device)
+    k = h.num_perm
+    dt = np.uint64 if out_u64 else np.uint32
+    if out is None:
+        out = np.empty((n, k), dtype=dt)
+    elif out.dtype != dt or out.shape != (n, k) or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous [n_docs, num_perm] array of dtype %s" % dt)
+    init_p, init_stride, init64 = None, 0, 0
+    if init is not None:
+        init = np.ascontiguousarray(init)
+        if init.dtype not in (np.uint32, np.uint64):
+            init = init.astype(np.uint64)
+        init64 = int(init.dtype == np.uint64)
+        if init.ndim == 1:
+            if init.shape[0] != k:
+                raise ValueError("init row length mismatch")
+            init_stride = 0
+        else:
+            if init.shape != (n, k):
+                raise ValueError("init must be [num_perm] or [n_docs, num_perm]")
+            init_stride = k
+        init_p = init.ctypes.data
+    if n == 0:
+        return out
+    nv.check(nv.load().dsk_minhash_bulk_host(h.handle, tok.ctypes.data if tok.size else None, is64, off.ctypes.data,
+                                              n, init_p, init_stride, init64, out.ctypes.data, int(out_u64),
+                                              KERNELS[kernel]))
+    return out
+
+
+def bulk_signatures_device(d_tokens, d_offsets, n_tokens: int, permutations: np.ndarray, d_out=None, d_init=None,
+                           init_stride: int = 0, kernel: str = "auto", stream: Optional[int] = None):
+    """DEVICE buffers in (torch CUDA tensors: uint32/int32 or uint64/int64 tokens, int64 offsets),
+    DEVICE [N, K] signature tensor out.  Asynchronous on ``stream`` (default: torch's current stream)."""
+    import torch
+    dev = d_tokens.device.index if d_tokens.is_cuda else None
+    if dev is None or not d_offsets.is_cuda:
+        raise ValueError("bulk_signatures_device needs CUDA tensors")
+    is64 = int(d_tokens.element_size() == 8)
+    n = d_offsets.numel() - 1
+    h = nv.perm_handle(permutations, dev)
+    k = h.num_perm
+    if d_out is None:
+        d_out = torch.empty((n, k), dtype=torch.int32, device=d_tokens.device)
+    out64 = int(d_out.element_size() == 8)
+    if stream is None:
+        stream = torch.cuda.current_stream(d_tokens.device).cuda_stream
+    with torch.cuda.device(dev):
+        nv.check(nv.load().dsk_minhash_bulk(h.handle, d_tokens.data_ptr() if n_tokens else None, is64,
+                                             d_offsets.data_ptr(), n, n_tokens,
+                                             d_init.data_ptr() if d_init is not None else None, init_stride,
+                                             int(d_init.element_size() == 8) if d_init is not None else 0,
+                                             d_out.data_ptr(), out64, KERNELS[kernel], stream))
+    return d_out

@@ -1,0 +1,113 @@
+/* dsk.h -- C-ABI of libdsk_b200.so: the B200 (sm_100a) MinHash / LSH signature engine.
+ *
+ * The reference (ekzhu/datasketch 1.10.0) is pure Python and exposes NO plugin /
+ * FFI interface; its only backend seam is the `gpu_mode` switch inside
+ * MinHash.update_batch (datasketch/minhash.py:117, :270-291).  This header is the
+ * boundary a maintainer would bind with ctypes to replace that seam and the
+ * Python loops around it (see INTEGRATION.md for the stub).  Each entry point
+ * cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (streams are void*,
+ *     i.e. a cudaStream_t / CUstream value; NULL = the legacy default stream).
+ *   - "d_" parameters are DEVICE pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); "h_" parameters are HOST pointers.
+ *   - device entry points are stream-ordered and asynchronous; return 0 when the
+ *     work was enqueued, non-zero DSK_ERR_* otherwise; dsk_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - integer results are bit-exact with the reference's numpy uint64 path.
+ */
+#ifndef DSK_H_
+#define DSK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSK_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define DSK_API __attribute__((visibility("default")))
+#else
+#define DSK_API
+#endif
+
+enum {
+    DSK_OK = 0,
+    DSK_ERR_INVALID = 1,   /* bad argument (maps to ValueError in the Python host layer) */
+    DSK_ERR_CUDA = 2,      /* CUDA runtime error (maps to RuntimeError) */
+    DSK_ERR_NO_DEVICE = 3, /* no sm_100 device: there is NO CPU fallback (RuntimeError) */
+    DSK_ERR_ALIGN = 4,     /* pointer alignment contract violated */
+    DSK_ERR_NOMEM = 5
+};
+
+/* kernel selection for dsk_minhash_bulk (flags) */
+enum {
+    DSK_KERNEL_AUTO = 0,     /* two-phase kernel when it is exact for (perm, token width), else exact */
+    DSK_KERNEL_TWO_PHASE = 1,/* force; returns DSK_ERR_INVALID if not exact for this handle / token width */
+    DSK_KERNEL_DIRECT = 2,   /* one full evaluation per (token, perm), no candidate filtering */
+    DSK_KERNEL_EXACT = 3     /* full 64-bit `% (2^61-1)` per evaluation; any permutation, u32/u64 tokens */
+};
+
+DSK_API int dsk_version(void);
+DSK_API const char *dsk_last_error(void);
+
+/* Number of usable CUDA devices; *sm_count / *cc receive properties of `device`.
+ * Replaces datasketch/minhash.py:38-48 (_gpu_available). */
+DSK_API int dsk_device_count(void);
+DSK_API int dsk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+
+/* ---- permutation handle -------------------------------------------------------
+ * Uploads the (a, b) parameters of MinHash._init_permutations
+ * (datasketch/minhash.py:170-184; generated on the HOST with numpy, never on
+ * device) and analyses them once: `n_unsafe` = number of permutations for which
+ * some 32-bit token value h makes ((a*h+b) mod 2^64) fall in the 36-value set
+ * where `% (2^61-1)` needs its conditional subtract.  The two-phase / direct
+ * kernels are bit-exact iff n_unsafe == 0 (otherwise AUTO picks the exact kernel).
+ * Replaces minhash.py:160-165 (_ensure_gpu_caches). */
+typedef struct dsk_perm dsk_perm;
+DSK_API int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int device, dsk_perm **out);
+DSK_API int dsk_perm_info(const dsk_perm *p, int *num_perm, int *n_unsafe, int *device);
+DSK_API void dsk_perm_destroy(dsk_perm *p);
+/* Host-only analysis (no device needed): out_unsafe[i] = 1 iff permutation i can reach the
+ * conditional-subtract set with some token h < 2^32.  Returns the number of unsafe ones. */
+DSK_API int dsk_perm_analyze(const uint64_t *h_a, const uint64_t *h_b, int num_perm, uint8_t *out_unsafe);
+
+/* ---- bulk signature build -------------------------------------------------------
+ * Replaces MinHash.update_batch's hot loop (datasketch/minhash.py:294-297 CPU,
+ * :281-291 CuPy) batched over documents as in MinHash.bulk / generator
+ * (:464-522): for document i with token hashes tokens[offsets[i]:offsets[i+1]],
+ *   out[i][k] = min(init[i][k], min_t (((a_k*h_t + b_k) mod 2^64) % (2^61-1)) & 0xFFFFFFFF)
+ * d_tokens   u32 (token_is_u64=0) or u64 (=1) token hashes, 16-byte aligned
+ * d_offsets  int64[n_docs+1], non-decreasing CSR offsets, offsets[n_docs] == n_tokens
+ * d_init     NULL (empty state, all 0xFFFFFFFF: minhash.py:167-168) or running
+ *            signatures to merge (update_batch on a non-empty MinHash, :297);
+ *            init_stride = elements between rows (0 = one row broadcast to all docs)
+ * d_out      [n_docs, num_perm] u32 (out_is_u64=0) or u64 (=1; the reference's dtype)
+ * flags      DSK_KERNEL_*  */
+DSK_API int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u64,
+                     const int64_t *d_offsets, int64_t n_docs, int64_t n_tokens,
+                     const void *d_init, int64_t init_stride, int init_is_u64,
+                     void *d_out, int out_is_u64, int flags, void *stream);
+
+/* Host-buffer variant: same computation, tokens/offsets/out are HOST pointers
+ * (pinned memory gives full PCIe overlap; pageable memory is staged).  Documents
+ * are cut into slices and H2D copy, kernel and D2H copy are pipelined over
+ * internal streams; returns after the last slice landed in h_out.
+ * This is the call the reference-facing MinHash.bulk makes. */
+DSK_API int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_is_u64,
+                          const int64_t *h_offsets, int64_t n_docs,
+                          const void *h_init, int64_t init_stride, int init_is_u64,
+                          void *h_out, int out_is_u64, int flags);
+
+/* Element-wise min of two signature matrices (MinHash.merge / union,
+ * datasketch/minhash.py:359, :453; LeanMinHash.union lean_minhash.py:249). */
+DSK_API int dsk_sig_merge_min(const uint32_t *d_x, const uint32_t *d_y, int64_t n_elems, uint32_t *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSK_H_ */

@@ -1,0 +1,239 @@
+"""GPU parity tests for the bulk signature path: CUDA kernels (through the C-ABI)
+vs fixtures produced by the real reference and vs the oracle on seeded inputs."""
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import oracle_clib as oc
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["two_phase", "direct", "exact"]
+
+
+@pytest.fixture(scope="module")
+def dsk():
+    import datasketch_b200
+    return datasketch_b200
+
+
+def test_reference_absolute_golden(dsk):
+    # test/test_minhash.py:109-115 of the reference
+    m = dsk.MinHash(4, 1)
+    m.update(b"Hello")
+    assert m.hashvalues.tolist() == [734825475, 960773806, 359816889, 342714745]
+    assert m.hashvalues.dtype == np.uint64
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c1_bulk_golden(dsk, golden, kernel):
+    g = golden("minhash")
+    tok = g["c1_tokens"].reshape(-1)
+    off = np.arange(1001, dtype=np.int64) * 64
+    P = o.init_permutations(128, 1)
+    sig = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel)
+    assert sig.dtype == np.uint32 and np.array_equal(sig, g["c1_sig"])
+    sig64 = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel, out_u64=True)
+    assert sig64.dtype == np.uint64 and np.array_equal(sig64, g["c1_sig"].astype(np.uint64))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("k", [4, 33, 100, 128, 256])
+def test_ragged_golden(dsk, golden, k, kernel):
+    g = golden("minhash")
+    tok, off, seed = g[f"rag_k{k}_tokens"], g[f"rag_k{k}_offsets"], int(g[f"rag_k{k}_seed"])
+    P = o.init_permutations(k, seed)
+    sig = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel)
+    assert np.array_equal(sig, g[f"rag_k{k}_sig"])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_long_and_small_docs(dsk, golden, kernel):
+    g = golden("minhash")
+    P = o.init_permutations(128, 1)
+    sig = dsk.engine.bulk_signatures(g["long_tokens"], np.array([0, 20000]), P, kernel=kernel)
+    assert np.array_equal(sig, g["long_sig"])
+    sig = dsk.engine.bulk_signatures(g["small_tokens"], np.array([0, 64]), P, kernel=kernel)
+    assert np.array_equal(sig, g["small_sig"])
+
+
+def test_u64_tokens_golden(dsk, golden):
+    g = golden("minhash")
+    P = o.init_permutations(64, 3)
+    sig = dsk.engine.bulk_signatures(g["u64_tokens"], g["u64_offsets"], P, out_u64=True)
+    assert np.array_equal(sig, g["u64_sig"])
+    with pytest.raises(ValueError):  # fast kernels are not exact for 64-bit hashes
+        dsk.engine.bulk_signatures(g["u64_tokens"], g["u64_offsets"], P, kernel="two_phase")
+
+
+def test_sha1_update_batch_like_reference_gpu_test(dsk, golden):
+    # shapes of test/test_minhash_gpu.py:26-52 of the reference
+    g = golden("minhash")
+    data = [f"token-{i}".encode() for i in range(1000)]
+    m = dsk.MinHash(num_perm=256, seed=7, gpu_mode="always")
+    m.update_batch(data)
+    assert np.array_equal(m.hashvalues, g["sha1_k256_s7_n1000"])
+    m = dsk.MinHash(num_perm=128, seed=7, gpu_mode="detect")
+    m.update_batch(data[:500])
+    m.update_batch(data[:700])
+    assert np.array_equal(m.hashvalues, g["sha1_k128_s7_500_700"])
+
+
+def test_update_equals_update_batch_equals_bulk(dsk):
+    ident = int
+    m1 = dsk.MinHash(4, 1, hashfunc=ident)
+    m1.update(12)
+    m1.update(24)
+    m2 = dsk.MinHash(4, 1, hashfunc=ident)
+    m2.update_batch([12, 24])
+    assert all(m1.hashvalues == m2.hashvalues)
+    kwargs = dict(num_perm=4, seed=1, hashfunc=ident)
+    b = [[n * 4 for n in range(4)]] * 2
+    m = dsk.MinHash(**kwargs)
+    m.update_batch(b[0])
+    x, y = dsk.MinHash.bulk(b, **kwargs)
+    assert np.array_equal(m.hashvalues, x.hashvalues) and np.array_equal(m.hashvalues, y.hashvalues)
+    want = o.update_batch(o.init_hashvalues(4), b[0], o.init_permutations(4, 1))
+    assert np.array_equal(m.hashvalues, want)
+
+
+def test_running_state_merge_and_estimators(dsk, golden):
+    g = golden("minhash")
+    m1 = dsk.MinHash(num_perm=128, seed=1, hashfunc=int)
+    m1.update_batch(range(0, 100))
+    _ = m1.hashvalues  # flush, then continue on a non-empty state (minhash.py:297)
+    m1.update_batch(range(100, 300))
+    m2 = dsk.MinHash(num_perm=128, seed=1, hashfunc=int)
+    m2.update_batch(range(150, 450))
+    assert np.array_equal(m1.hashvalues, g["j_m1"]) and np.array_equal(m2.hashvalues, g["j_m2"])
+    assert m1.jaccard(m2) == float(g["j_jaccard"])
+    assert m1.count() == float(g["j_count1"])
+    assert np.array_equal(dsk.MinHash.union(m1, m2).hashvalues, g["j_union"])
+    mm = m1.copy()
+    mm.merge(m2)
+    assert np.array_equal(mm.hashvalues, g["j_merge"])
+    p = pickle.loads(pickle.dumps(m1))
+    assert p.seed == m1.seed and np.array_equal(p.hashvalues, m1.hashvalues)
+    assert np.array_equal(p.permutations, m1.permutations)
+
+
+def test_init_matrix_and_broadcast(dsk):
+    rs = np.random.RandomState(3)
+    P = o.init_permutations(128, 9)
+    tok = rs.randint(0, 2 ** 32, size=50 * 40, dtype=np.uint64).astype(np.uint32)
+    off = np.arange(51, dtype=np.int64) * 40
+    base = dsk.engine.bulk_signatures(tok, off, P)
+    tok2 = rs.randint(0, 2 ** 32, size=50 * 40, dtype=np.uint64).astype(np.uint32)
+    both = dsk.engine.bulk_signatures(tok2, off, P, init=base)
+    want = np.minimum(base, oc.minhash_bulk_u32tok(tok2, off, P))
+    assert np.array_equal(both, want)
+    row = base[7].astype(np.uint64)
+    bc = dsk.engine.bulk_signatures(tok2, off, P, init=row, out_u64=True)
+    assert np.array_equal(bc, np.minimum(row[None, :], oc.minhash_bulk_u32tok(tok2, off, P).astype(np.uint64)))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_tail_and_alignment_shapes(dsk, kernel):
+    # total token counts that are not multiples of 4 / 16 exercise the non-TMA tail path
+    rs = np.random.RandomState(5)
+    P = o.init_permutations(128, 1)
+    for n_tok in [1, 2, 3, 5, 15, 17, 31, 33, 511, 513, 1023, 2049]:
+        tok = rs.randint(0, 2 ** 32, size=n_tok, dtype=np.uint64).astype(np.uint32)
+        cuts = np.sort(rs.randint(0, n_tok + 1, size=5))
+        off = np.concatenate([[0], cuts, [n_tok]]).astype(np.int64)
+        sig = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel)
+        assert np.array_equal(sig, oc.minhash_bulk_u32tok(tok, off, P)), n_tok
+
+
+def test_duplicates_and_near_ties_take_slow_path(dsk):
+    # small multipliers make many L' values collide / land within the +7 window and < 7
+    rs = np.random.RandomState(8)
+    a = rs.randint(1, 64, size=128).astype(np.uint64)
+    a[::4] |= rs.randint(0, 2 ** 29, size=32).astype(np.uint64) << np.uint64(32)
+    b = rs.randint(0, 200, size=128).astype(np.uint64)
+    b[1::2] = rs.randint(0, 2 ** 61 - 1, size=64, dtype=np.uint64)
+    P = np.stack([a, b])
+    from datasketch_b200 import _native as nv
+    docs = []
+    for i in range(200):
+        t = rs.randint(0, 64 if i % 2 else 2 ** 32, size=rs.randint(1, 150), dtype=np.uint64)
+        if i % 3 == 0:
+            t[rs.randint(0, len(t), size=len(t) // 2)] = t[0]
+        docs.append(t.astype(np.uint32))
+    off = np.zeros(len(docs) + 1, dtype=np.int64)
+    np.cumsum([len(d) for d in docs], out=off[1:])
+    tok = np.concatenate(docs)
+    want = oc.minhash_bulk_u32tok(tok, off, P)
+    h = nv.perm_handle(P)
+    kernels = ["auto", "exact"] + (["two_phase", "direct"] if h.n_unsafe == 0 else [])
+    for kernel in kernels:
+        assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel=kernel), want), kernel
+
+
+def test_unsafe_permutations_route_to_exact(dsk):
+    # x = a*h + b can hit the 36 values where `% (2^61-1)` subtracts: the fast formula would be
+    # off by one there, so the handle must flag it and AUTO must stay bit-exact.
+    from datasketch_b200 import _native as nv
+    p = (1 << 61) - 1
+    a = np.array([1, 1, 3, 0, 1 << 40, 5], dtype=np.uint64)
+    b = np.array([p - 5, (7 << 61) + p - 9, p - 30, p, 12345, (3 << 61) + p - 2 - 5 * 77], dtype=np.uint64)
+    P = np.stack([a, b])
+    h = nv.perm_handle(P)
+    assert h.n_unsafe >= 4
+    tok = np.array([0, 1, 2, 5, 9, 10, 77, 1 << 24, 2 ** 32 - 1], dtype=np.uint32)
+    off = np.array([0, 3, 3, 9], dtype=np.int64)
+    want = o.bulk_signatures_csr(tok, off, 6, 0, permutations=P).astype(np.uint32)
+    assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P), want)
+    assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel="exact"), want)
+    with pytest.raises(ValueError):
+        dsk.engine.bulk_signatures(tok, off, P, kernel="two_phase")
+    # the values the fast formula would get wrong are really exercised:
+    hits = [(int(ai) * int(t) + int(bi)) % (1 << 64) for ai, bi in zip(a, b) for t in tok]
+    assert any(((x & p) + (x >> 61)) >= p for x in hits)
+
+
+def test_seeded_permutations_are_safe(dsk):
+    from datasketch_b200 import _native as nv
+    for k, seed in [(128, 1), (256, 7), (512, 123)]:
+        assert nv.perm_handle(o.init_permutations(k, seed)).n_unsafe == 0
+
+
+def test_device_buffer_api(dsk):
+    import torch
+    rs = np.random.RandomState(12)
+    P = o.init_permutations(128, 1)
+    tok = rs.randint(0, 2 ** 32, size=300 * 77, dtype=np.uint64).astype(np.uint32)
+    off = np.arange(301, dtype=np.int64) * 77
+    d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    d_sig = dsk.engine.bulk_signatures_device(d_tok, d_off, tok.size, P)
+    torch.cuda.synchronize()
+    got = d_sig.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, oc.minhash_bulk_u32tok(tok, off, P))
+    # misaligned token pointer is rejected, not silently mis-read
+    with pytest.raises(ValueError):
+        dsk.engine.bulk_signatures_device(d_tok[1:], d_off, tok.size - 1, P)
+
+
+@pytest.mark.parametrize("kernel", ["two_phase", "direct"])
+def test_medium_batch_sampled_against_oracle(dsk, kernel):
+    # 50k docs x 256 tokens (C2 shape, scaled): every 97th document checked against the C oracle
+    rs = np.random.RandomState(0)
+    n, t = 50_000, 256
+    tok = rs.randint(0, 2 ** 32, size=n * t, dtype=np.uint64).astype(np.uint32)
+    off = np.arange(n + 1, dtype=np.int64) * t
+    P = o.init_permutations(128, 1)
+    sig = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel)
+    idx = np.arange(0, n, 97)
+    sub_off = np.arange(len(idx) + 1, dtype=np.int64) * t
+    sub_tok = tok.reshape(n, t)[idx].reshape(-1)
+    assert np.array_equal(sig[idx], oc.minhash_bulk_u32tok(sub_tok, sub_off, P))
+    # size-independent properties: permuting tokens inside a document, or duplicating them,
+    # does not change its signature; splitting a document and min-merging the halves does not either
+    perm_tok = tok.reshape(n, t)[:, ::-1].reshape(-1).copy()
+    assert np.array_equal(dsk.engine.bulk_signatures(perm_tok, off, P, kernel=kernel), sig)
+    half = np.arange(2 * n + 1, dtype=np.int64) * (t // 2)
+    parts = dsk.engine.bulk_signatures(tok, half, P, kernel=kernel)
+    assert np.array_equal(np.minimum(parts[0::2], parts[1::2]), sig)
