@@ -177,67 +177,98 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
     };
 
     // ---- documents ---------------------------------------------------------------------
+    constexpr int kLogBlkPerChunk = (kBlkPerChunk == 32) ? 5 : (kBlkPerChunk == 16) ? 4 : -1;
+    static_assert(kLogBlkPerChunk > 0 && (1 << kLogBlkPerChunk) == kBlkPerChunk, "chunk/block geometry");
+
     int64_t start = tok_lo;
     for (int64_t d = dlo; d < dhi; ++d) {
         const int64_t end = __ldg(offsets + d + 1);
 
-        uint32_t m[P], m2[P], widx[P];  // TWO_PHASE: min L', 2nd-smallest block min, winning block
+        // TWO_PHASE: m = min L', m2 = 2nd-smallest block min, widx = winning block (doc-local).
+        // DIRECT / EXACT: m = running signature.
+        uint32_t m[P], m2[P], widx[P];
 #pragma unroll
         for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; widx[j] = 0; }
 
+        // one 16-token block, tokens already in registers (the hot code: 64 IMAD + 32 VIMNMX3 for P=4)
+        auto process = [&](const TokT *src, uint32_t lb) {
+            TokT t[kBlkTok];
+            TokLoad<TokT>::block(src, t);
+            if constexpr (MODE == MODE_TWO_PHASE) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const uint32_t c7 = blo[j] + 7u;
+                    uint32_t bm = umin3(alo[j] * (uint32_t)t[0] + c7, alo[j] * (uint32_t)t[1] + c7,
+                                        alo[j] * (uint32_t)t[2] + c7);
+#pragma unroll
+                    for (int i = 3; i < kBlkTok - 1; i += 2)
+                        bm = umin3(bm, alo[j] * (uint32_t)t[i] + c7, alo[j] * (uint32_t)t[i + 1] + c7);
+                    bm = min(bm, alo[j] * (uint32_t)t[kBlkTok - 1] + c7);
+                    const uint32_t om = m[j];
+                    m2[j] = min(m2[j], max(bm, om));
+                    const bool lt = bm < om;
+                    m[j] = lt ? bm : om;
+                    widx[j] = lt ? lb : widx[j];
+                }
+            } else if constexpr (MODE == MODE_DIRECT) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+#pragma unroll
+                    for (int i = 0; i < kBlkTok; i += 2)
+                        m[j] = umin3(m[j], eval_fast(alo[j], ahi[j], b64, (uint32_t)t[i]),
+                                     eval_fast(alo[j], ahi[j], b64, (uint32_t)t[i + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const uint64_t a64 = ((uint64_t)ahi[j] << 32) | alo[j];
+                    const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+#pragma unroll 4
+                    for (int i = 0; i < kBlkTok; ++i) m[j] = min(m[j], eval_exact(a64, b64, (uint64_t)t[i]));
+                }
+            }
+        };
+
         if (end > start) {
-            const int64_t bfirst = start / kBlkTok, blast = (end - 1) / kBlkTok;
-            for (int64_t blk = bfirst; blk <= blast; ++blk) {
-                map_chunk((blk - blk_begin) / kBlkPerChunk);
+            const int64_t dblk0 = start / kBlkTok, blast = (end - 1) / kBlkTok;
+            const bool head_cut = (start % kBlkTok) != 0, tail_cut = (end % kBlkTok) != 0;
+            int64_t blk = dblk0;
+            while (blk <= blast) {
+                map_chunk((blk - blk_begin) >> kLogBlkPerChunk);
                 const int64_t cblk0 = blk_begin + cur * kBlkPerChunk;
                 const TokT *cbuf = reinterpret_cast<const TokT *>(s_buf[warp][cur % kNBuf]);
-                const TokT *src = cbuf + (blk - cblk0) * kBlkTok;
-                const bool partial = (blk * kBlkTok < start) || (blk * kBlkTok + kBlkTok > end);
-                if (partial) {
-                    // boundary block: out-of-document slots are replaced by a duplicate of an
-                    // in-document token (min is idempotent), then the block is handled uniformly
+                // this document's run of blocks inside the mapped chunk, in 32-bit chunk-local terms
+                const int nb = (int)(min(blast + 1, cblk0 + kBlkPerChunk) - blk);
+                const TokT *p = cbuf + (int)(blk - cblk0) * kBlkTok;
+                const uint32_t lb0 = (uint32_t)(blk - dblk0);
+                const bool hp = head_cut && blk == dblk0;           // first block starts mid-block
+                const bool tp = tail_cut && blk + nb - 1 == blast;  // last block ends mid-block
+
+                // boundary block: out-of-document slots are replaced by a duplicate of an in-document
+                // token (min is idempotent) in a per-warp scratch line, then handled like any other
+                auto patched = [&](int i) {
                     if (lane < kBlkTok) {
-                        int64_t i = blk * kBlkTok + lane;
-                        i = max(start, min(i, end - 1));
-                        s_scratch[warp][lane] = cbuf[i - cblk0 * kBlkTok];
+                        int64_t q = (blk + i) * kBlkTok + lane;
+                        q = max(start, min(q, end - 1));
+                        s_scratch[warp][lane] = cbuf[q - cblk0 * kBlkTok];
                     }
                     __syncwarp();
-                    src = s_scratch[warp];
+                    process(s_scratch[warp], lb0 + (uint32_t)i);
+                    __syncwarp();
+                };
+                int i = 0;
+                if (hp || (tp && nb == 1)) { patched(0); i = 1; }
+                const int nfull = (tp && nb > 1) ? nb - 1 : nb;
+                {   // tight loop over whole blocks: pointer bump + 32-bit counter only
+                    const TokT *q = p + i * kBlkTok;
+                    const TokT *const qe = p + nfull * kBlkTok;
+                    uint32_t lb = lb0 + (uint32_t)i;
+#pragma unroll 1
+                    for (; q < qe; q += kBlkTok, ++lb) process(q, lb);
                 }
-                TokT t[kBlkTok];
-                TokLoad<TokT>::block(src, t);
-                if (partial) __syncwarp();  // scratch may be rewritten by the next block
-
-                if constexpr (MODE == MODE_TWO_PHASE) {
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const uint32_t c7 = blo[j] + 7u;
-                        uint32_t bm = 0xFFFFFFFFu;
-#pragma unroll
-                        for (int i = 0; i < kBlkTok; i += 2)
-                            bm = umin3(bm, alo[j] * (uint32_t)t[i] + c7, alo[j] * (uint32_t)t[i + 1] + c7);
-                        const uint32_t om = m[j];
-                        m2[j] = min(m2[j], max(bm, om));
-                        if (bm < om) { m[j] = bm; widx[j] = (uint32_t)blk; }
-                    }
-                } else if constexpr (MODE == MODE_DIRECT) {
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
-#pragma unroll
-                        for (int i = 0; i < kBlkTok; i += 2)
-                            m[j] = umin3(m[j], eval_fast(alo[j], ahi[j], b64, (uint32_t)t[i]),
-                                         eval_fast(alo[j], ahi[j], b64, (uint32_t)t[i + 1]));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const uint64_t a64 = ((uint64_t)ahi[j] << 32) | alo[j];
-                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
-#pragma unroll 4
-                        for (int i = 0; i < kBlkTok; ++i) m[j] = min(m[j], eval_exact(a64, b64, (uint64_t)t[i]));
-                    }
-                }
+                if (tp && nb > 1) patched(nb - 1);
+                blk += nb;
             }
         }
 
@@ -250,11 +281,22 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
                 uint32_t r = 0xFFFFFFFFu;
                 if (end > start) {
                     const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
-                    const int64_t base = (int64_t)widx[j] * kBlkTok;
+                    const int64_t base = (start / kBlkTok + (int64_t)widx[j]) * kBlkTok;
+                    if (base >= start && base + kBlkTok <= end) {
+                        // whole block inside the document (and thus inside the array): 4 x LDG.128
+                        const uint4 *q = reinterpret_cast<const uint4 *>(tokens + base);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 v = __ldg(q + i);
+                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v.x), eval_fast(alo[j], ahi[j], b64, v.y));
+                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v.z), eval_fast(alo[j], ahi[j], b64, v.w));
+                        }
+                    } else {
 #pragma unroll 4
-                    for (int i = 0; i < kBlkTok; ++i) {
-                        const int64_t p = max(start, min(base + i, end - 1));
-                        r = min(r, eval_fast(alo[j], ahi[j], b64, (uint32_t)__ldg(tokens + p)));
+                        for (int i = 0; i < kBlkTok; ++i) {
+                            const int64_t p = max(start, min(base + i, end - 1));
+                            r = min(r, eval_fast(alo[j], ahi[j], b64, (uint32_t)__ldg(tokens + p)));
+                        }
                     }
                     // another block within the +7 window, or L'-7 could wrap: resolve exactly below
                     if (m[j] < 7u || (m2[j] - m[j]) <= 7u) need_slow |= 1u << j;
