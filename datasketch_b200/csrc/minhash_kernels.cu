@@ -31,7 +31,7 @@ namespace dsk {
 
 constexpr int kWarps = 4;           // warps per CTA
 constexpr int kChunkBytes = 2048;   // bytes per TMA bulk copy / ring slot
-constexpr int kNBuf = 2;            // ring depth per warp
+constexpr int kNBuf = 3;            // ring depth per warp: previous | current | next chunk
 constexpr int kBlkTok = 16;         // tokens per block (phase-1 tracking granularity)
 constexpr uint64_t kP61 = (1ull << 61) - 1;
 
@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
     static_assert(MODE == MODE_EXACT || sizeof(TokT) == 4, "fast paths need 32-bit token hashes");
     constexpr int kBlkBytes = kBlkTok * (int)sizeof(TokT);
     constexpr int kBlkPerChunk = kChunkBytes / kBlkBytes;
+    constexpr int kLogBlkPerChunk = (kBlkPerChunk == 32) ? 5 : (kBlkPerChunk == 16) ? 4 : -1;
+    static_assert(kLogBlkPerChunk > 0 && (1 << kLogBlkPerChunk) == kBlkPerChunk, "chunk/block geometry");
+    static_assert(kNBuf == 3, "ring = previous | current | next chunk");
 
     __shared__ __align__(128) unsigned char s_buf[kWarps][kNBuf][kChunkBytes];
     __shared__ __align__(16) TokT s_scratch[kWarps][kBlkTok];
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
         blo[j] = __ldg(prm.b_lo + kl + j); bhi[j] = __ldg(prm.b_hi + kl + j);
     }
 
-    // ---- per-warp TMA ring --------------------------------------------------------------
+    // ---- per-warp TMA ring: previous | current | next chunk ---------------------------------
     const int64_t tok_lo = __ldg(offsets + dlo), tok_hi = __ldg(offsets + dhi);
     const int64_t blk_begin = tok_lo / kBlkTok;
     const int64_t blk_end = (tok_hi + kBlkTok - 1) / kBlkTok;
@@ -152,37 +155,41 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
         }
     };
     if (lane == 0) {
-        for (int64_t c = 0; c < min(nchunks, (int64_t)kNBuf); ++c) issue(c);
+        for (int64_t c = 0; c < min(nchunks, (int64_t)2); ++c) issue(c);
     }
 
-    int64_t cur = 0;     // chunk currently mapped
-    bool ready = false;  // cur has been waited on
+    int64_t cur = 0;           // chunk currently mapped
+    int cur_slot = 0;          // == cur % 3
+    int prev_slot = kNBuf - 1; // == (cur - 1) % 3 (only meaningful when cur >= 1)
+    uint32_t cur_par = 0;      // == (cur / 3) & 1
+    bool ready = false;        // cur has been waited on
     auto map_chunk = [&](int64_t c) {
         while (cur < c) {
-            __syncwarp();  // every lane is done reading slot cur % kNBuf
-            if (lane == 0 && cur + kNBuf < nchunks) issue(cur + kNBuf);
+            __syncwarp();  // every lane is done reading chunk cur-1, whose slot chunk cur+2 takes
+            if (lane == 0 && cur + 2 < nchunks) issue(cur + 2);
             ++cur;
+            prev_slot = cur_slot;
+            if (++cur_slot == kNBuf) { cur_slot = 0; cur_par ^= 1u; }
             ready = false;
         }
         if (!ready) {
-            mbar_wait(&bar[cur % kNBuf], (uint32_t)((cur / kNBuf) & 1));
+            mbar_wait(&bar[cur_slot], cur_par);
             // the last (< 16 B) tokens of the whole array cannot travel by bulk copy
             const int64_t c0 = (blk_begin + cur * kBlkPerChunk) * kBlkTok;
             const int64_t i = tail_tok + lane;
             if (i < n_tokens && i >= c0 && i < c0 + (int64_t)kBlkPerChunk * kBlkTok)
-                reinterpret_cast<TokT *>(s_buf[warp][cur % kNBuf])[i - c0] = tokens[i];
+                reinterpret_cast<TokT *>(s_buf[warp][cur_slot])[i - c0] = tokens[i];
             __syncwarp();
             ready = true;
         }
     };
 
     // ---- documents ---------------------------------------------------------------------
-    constexpr int kLogBlkPerChunk = (kBlkPerChunk == 32) ? 5 : (kBlkPerChunk == 16) ? 4 : -1;
-    static_assert(kLogBlkPerChunk > 0 && (1 << kLogBlkPerChunk) == kBlkPerChunk, "chunk/block geometry");
-
     int64_t start = tok_lo;
+    int64_t end_pref = __ldg(offsets + dlo + 1);  // offsets are read one document ahead
     for (int64_t d = dlo; d < dhi; ++d) {
-        const int64_t end = __ldg(offsets + d + 1);
+        const int64_t end = end_pref;
+        if (d + 1 < dhi) end_pref = __ldg(offsets + d + 2);
 
         // TWO_PHASE: m = min L', m2 = 2nd-smallest block min, widx = winning block (doc-local).
         // DIRECT / EXACT: m = running signature.
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
 #pragma unroll
         for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; widx[j] = 0; }
 
-        // one 16-token block, tokens already in registers (the hot code: 64 IMAD + 32 VIMNMX3 for P=4)
+        // one 16-token block (the hot code: 64 IMAD + 32 VIMNMX3 + 20 tracking ops for P=4)
         auto process = [&](const TokT *src, uint32_t lb) {
             TokT t[kBlkTok];
             TokLoad<TokT>::block(src, t);
@@ -230,14 +237,15 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
             }
         };
 
+        const int64_t dblk0 = start / kBlkTok;
         if (end > start) {
-            const int64_t dblk0 = start / kBlkTok, blast = (end - 1) / kBlkTok;
+            const int64_t blast = (end - 1) / kBlkTok;
             const bool head_cut = (start % kBlkTok) != 0, tail_cut = (end % kBlkTok) != 0;
             int64_t blk = dblk0;
             while (blk <= blast) {
                 map_chunk((blk - blk_begin) >> kLogBlkPerChunk);
                 const int64_t cblk0 = blk_begin + cur * kBlkPerChunk;
-                const TokT *cbuf = reinterpret_cast<const TokT *>(s_buf[warp][cur % kNBuf]);
+                const TokT *cbuf = reinterpret_cast<const TokT *>(s_buf[warp][cur_slot]);
                 // this document's run of blocks inside the mapped chunk, in 32-bit chunk-local terms
                 const int nb = (int)(min(blast + 1, cblk0 + kBlkPerChunk) - blk);
                 const TokT *p = cbuf + (int)(blk - cblk0) * kBlkTok;
@@ -277,31 +285,62 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
         if constexpr (MODE == MODE_TWO_PHASE) {
             unsigned need_slow = 0;
 #pragma unroll
-            for (int j = 0; j < P; ++j) {
-                uint32_t r = 0xFFFFFFFFu;
-                if (end > start) {
-                    const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
-                    const int64_t base = (start / kBlkTok + (int64_t)widx[j]) * kBlkTok;
-                    if (base >= start && base + kBlkTok <= end) {
-                        // whole block inside the document (and thus inside the array): 4 x LDG.128
-                        const uint4 *q = reinterpret_cast<const uint4 *>(tokens + base);
+            for (int j = 0; j < P; ++j) res[j] = 0xFFFFFFFFu;
+            if (end > start) {
+                // phase 2: exact evaluation of each permutation's winning block.  Fast path: every lane's
+                // winners are whole blocks still resident in the ring (previous | current chunk) -> LDS.128.
+                const uint32_t *src[P];
+                bool fast = true;
+                unsigned res_mask = 0;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 v = __ldg(q + i);
-                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v.x), eval_fast(alo[j], ahi[j], b64, v.y));
-                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v.z), eval_fast(alo[j], ahi[j], b64, v.w));
-                        }
-                    } else {
-#pragma unroll 4
-                        for (int i = 0; i < kBlkTok; ++i) {
-                            const int64_t p = max(start, min(base + i, end - 1));
-                            r = min(r, eval_fast(alo[j], ahi[j], b64, (uint32_t)__ldg(tokens + p)));
-                        }
-                    }
+                for (int j = 0; j < P; ++j) {
+                    const int64_t wb = dblk0 + (int64_t)widx[j];
+                    const int64_t wc = (wb - blk_begin) >> kLogBlkPerChunk;
+                    const bool whole = wb * kBlkTok >= start && wb * kBlkTok + kBlkTok <= end;
+                    const bool resident = (wc == cur) || (wc + 1 == cur);
+                    const int slot = (wc == cur) ? cur_slot : prev_slot;
+                    src[j] = reinterpret_cast<const uint32_t *>(s_buf[warp][slot]) +
+                             (int)(wb - (blk_begin + wc * kBlkPerChunk)) * kBlkTok;
+                    fast = fast && whole && resident;
+                    if (resident) res_mask |= 1u << j;
                     // another block within the +7 window, or L'-7 could wrap: resolve exactly below
                     if (m[j] < 7u || (m2[j] - m[j]) <= 7u) need_slow |= 1u << j;
                 }
-                res[j] = r;
+                if (__all_sync(0xFFFFFFFFu, fast)) {
+                    uint4 v[P][4];
+#pragma unroll
+                    for (int j = 0; j < P; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[j][i] = reinterpret_cast<const uint4 *>(src[j])[i];
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+                        uint32_t r = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v[j][i].x), eval_fast(alo[j], ahi[j], b64, v[j][i].y));
+                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v[j][i].z), eval_fast(alo[j], ahi[j], b64, v[j][i].w));
+                        }
+                        res[j] = r;
+                    }
+                } else {
+                    // some winner is a boundary block or has left the ring: clamped per-token reads
+                    // (duplicates of in-document tokens are harmless), from the ring when resident
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
+                        const int64_t base = (dblk0 + (int64_t)widx[j]) * kBlkTok;
+                        const bool in_ring = (res_mask >> j) & 1u;
+                        uint32_t r = 0xFFFFFFFFu;
+#pragma unroll 4
+                        for (int i = 0; i < kBlkTok; ++i) {
+                            const int64_t q = max(start, min(base + i, end - 1));
+                            const uint32_t h = in_ring ? src[j][(int)(q - base)] : (uint32_t)__ldg(tokens + q);
+                            r = min(r, eval_fast(alo[j], ahi[j], b64, h));
+                        }
+                        res[j] = r;
+                    }
+                }
             }
             if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
                 uint32_t rs[P];
@@ -311,8 +350,8 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
                     uint32_t t[kBlkTok];
 #pragma unroll
                     for (int i = 0; i < kBlkTok; ++i) {
-                        const int64_t p = max(start, min(blk * kBlkTok + i, end - 1));
-                        t[i] = (uint32_t)__ldg(tokens + p);
+                        const int64_t q = max(start, min(blk * kBlkTok + i, end - 1));
+                        t[i] = (uint32_t)__ldg(tokens + q);
                     }
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
@@ -360,7 +399,7 @@ __global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkPar
         } else {
             uint32_t *row = static_cast<uint32_t *>(prm.out) + d * (int64_t)K + kl;
             if (P == 4 && (K & 3) == 0) {
-                if (kl < K) *reinterpret_cast<uint4 *>(row) = make_uint4(res[0], res[1], res[2 % P], res[3 % P]);
+                if (kl < K) *reinterpret_cast<uint4 *>(row) = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
             } else if (P == 8 && (K & 7) == 0) {
                 if (kl < K) {
                     reinterpret_cast<uint4 *>(row)[0] = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
