@@ -11,7 +11,8 @@ _native.load()  # fail loudly if the CUDA library is absent
 
 from .hashfunc import sha1_hash32, sha1_hash64  # noqa: E402
 from .minhash import MinHash  # noqa: E402
-from . import engine  # noqa: E402
+from .lean_minhash import LeanMinHash  # noqa: E402
+from . import codec, engine  # noqa: E402
 
 __version__ = "0.1.0"
-__all__ = ["MinHash", "sha1_hash32", "sha1_hash64", "engine"]
+__all__ = ["MinHash", "LeanMinHash", "sha1_hash32", "sha1_hash64", "engine", "codec"]

@@ -41,6 +41,10 @@ SIGNATURES = {
     "dsk_minhash_bulk_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_void_p, c_int, c_int]),
     "dsk_sig_merge_min": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dsk_lean_pack": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "dsk_lean_unpack": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "dsk_band_keys": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsk_band_fingerprints": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

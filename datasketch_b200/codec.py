@@ -1,0 +1,108 @@
+"""Batch codecs over device-resident signature matrices (torch CUDA tensors as buffers).
+
+``lean_pack`` / ``lean_unpack``: [N, K] signatures <-> LeanMinHash records
+(``struct`` "<bo> q i {K}I", datasketch/lean_minhash.py:174-175, :201-214).
+``band_keys``: the big-endian byte keys ``MinHashLSH._H`` builds per band
+(datasketch/lsh.py:344, :537-538).  ``band_fingerprints``: 64-bit bucket ids.
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+from . import _native as nv
+
+_BIG = {">": 1, "!": 1, "<": 0, "=": 0, "@": 0}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream(t, stream):
+    torch = _torch()
+    return torch.cuda.current_stream(t.device).cuda_stream if stream is None else stream
+
+
+def _as_device_sig(sig, device=0):
+    """numpy or torch, u32/u64 -> contiguous CUDA tensor (int32/int64 storage) + is_u64 flag."""
+    torch = _torch()
+    if isinstance(sig, np.ndarray):
+        if sig.dtype == np.uint32:
+            t = torch.from_numpy(np.ascontiguousarray(sig).view(np.int32))
+        elif sig.dtype == np.uint64:
+            t = torch.from_numpy(np.ascontiguousarray(sig).view(np.int64))
+        else:
+            raise TypeError("signature matrix must be uint32 or uint64")
+        nv.require_device(device)
+        sig = t.cuda(device)
+    if not sig.is_cuda or sig.dim() != 2:
+        raise ValueError("signature matrix must be a 2-D CUDA tensor")
+    return sig.contiguous(), int(sig.element_size() == 8)
+
+
+def lean_record_size(num_perm: int, byteorder: str = "@") -> int:
+    return struct.calcsize("%sqi%dI" % (byteorder, num_perm))
+
+
+def lean_pack(sig, seed: int, byteorder: str = "@", out=None, stream=None):
+    """[N, K] signatures -> [N, 12 + 4K] uint8 tensor of LeanMinHash records (one kernel)."""
+    torch = _torch()
+    d_sig, is64 = _as_device_sig(sig)
+    n, k = d_sig.shape
+    if lean_record_size(k, byteorder) != 12 + 4 * k:
+        raise ValueError("native struct layout on this platform is not the packed q|i|I layout")
+    if out is None:
+        out = torch.empty((n, 12 + 4 * k), dtype=torch.uint8, device=d_sig.device)
+    with torch.cuda.device(d_sig.device):
+        nv.check(nv.load().dsk_lean_pack(d_sig.data_ptr(), is64, n, k, int(seed), _BIG[byteorder], out.data_ptr(),
+                                         _stream(d_sig, stream)))
+    return out
+
+
+def lean_unpack(rec, num_perm: int, seed: int, byteorder: str = "@", out_u64: bool = False, stream=None):
+    """[N, 12 + 4K] uint8 records -> [N, K] signatures; raises ValueError if any header differs."""
+    torch = _torch()
+    if isinstance(rec, np.ndarray):
+        nv.require_device(0)
+        rec = torch.from_numpy(np.ascontiguousarray(rec)).cuda()
+    rec = rec.contiguous()
+    n = rec.shape[0]
+    if rec.numel() != n * (12 + 4 * num_perm):
+        raise ValueError("record buffer size does not match num_perm")
+    out = torch.empty((n, num_perm), dtype=torch.int64 if out_u64 else torch.int32, device=rec.device)
+    status = torch.zeros(1, dtype=torch.int32, device=rec.device)
+    with torch.cuda.device(rec.device):
+        nv.check(nv.load().dsk_lean_unpack(rec.data_ptr(), n, num_perm, int(seed), _BIG[byteorder], out.data_ptr(),
+                                           int(out_u64), status.data_ptr(), _stream(rec, stream)))
+    if int(status.item()) != 0:
+        raise ValueError("LeanMinHash record header (seed / num_perm) mismatch")
+    return out
+
+
+def band_keys(sig, b: int, r: int, stream=None):
+    """[N, K] u32 signatures -> [N, b, 8r] uint8 big-endian band keys (lsh.py:537-538)."""
+    torch = _torch()
+    d_sig, is64 = _as_device_sig(sig)
+    if is64:
+        raise TypeError("band_keys takes the 32-bit signature matrix")
+    n, k = d_sig.shape
+    out = torch.empty((n, b, 8 * r), dtype=torch.uint8, device=d_sig.device)
+    with torch.cuda.device(d_sig.device):
+        nv.check(nv.load().dsk_band_keys(d_sig.data_ptr(), n, k, b, r, out.data_ptr(), _stream(d_sig, stream)))
+    return out
+
+
+def band_fingerprints(sig, b: int, r: int, stream=None):
+    """[N, K] u32 signatures -> [N, b] int64 tensor holding the uint64 band fingerprints."""
+    torch = _torch()
+    d_sig, is64 = _as_device_sig(sig)
+    if is64:
+        raise TypeError("band_fingerprints takes the 32-bit signature matrix")
+    n, k = d_sig.shape
+    out = torch.empty((n, b), dtype=torch.int64, device=d_sig.device)
+    with torch.cuda.device(d_sig.device):
+        nv.check(nv.load().dsk_band_fingerprints(d_sig.data_ptr(), n, k, b, r, out.data_ptr(), _stream(d_sig, stream)))
+    return out

@@ -9,6 +9,8 @@
 //                            u64 (the dict keys MinHashLSH._H builds, lsh.py:344, :537-538).
 //  band_fingerprints       : [N,K] u32 -> [N, b] u64 mix of each band's r-tuple (GPU bucketing;
 //                            candidates are verified on the exact r-tuple, see lsh_kernels.cu).
+#include <algorithm>
+
 #include "dsk_common.cuh"
 
 namespace dsk {
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(kCodecThreads) lean_tile_kernel(const LeanPara
     uint32_t *sin[2] = {reinterpret_cast<uint32_t *>(smem), reinterpret_cast<uint32_t *>(smem) + in_words};
     uint32_t *sout[2] = {sin[1] + in_words, sin[1] + in_words + out_words};
     const uint32_t *gin = PACK ? p.sig : p.rec;
-    uint32_t *gout = PACK ? p.rec : p.sig;
+    uint32_t *gout = PACK ? p.rec : const_cast<uint32_t *>(p.sig);
     const int in_rw = PACK ? K : RW, out_rw = PACK ? RW : K;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kCodecThreads / 32;
@@ -226,11 +228,11 @@ cudaError_t launch_lean_pack(const void *sig, int sig_is_u64, int64_t n, int k, 
         cudaError_t e = cudaFuncSetAttribute(lean_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (n + R - 1) / R;
-        const int grid = (int)min<int64_t>(ntiles, (int64_t)sm_count * 2);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 2);
         lean_tile_kernel<true><<<grid, kCodecThreads, smem, s>>>(p);
     } else {
         const int64_t total = n * (k + 3);
-        const int grid = (int)min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
         lean_pack_simple_kernel<<<grid, 256, 0, s>>>(sig, sig_is_u64, n, k, w0, w1, w2, big_endian,
                                                      reinterpret_cast<uint32_t *>(rec));
     }
@@ -253,11 +255,11 @@ cudaError_t launch_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t see
         cudaError_t e = cudaFuncSetAttribute(lean_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (n + R - 1) / R;
-        const int grid = (int)min<int64_t>(ntiles, (int64_t)sm_count * 2);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 2);
         lean_tile_kernel<false><<<grid, kCodecThreads, smem, s>>>(p);
     } else {
         const int64_t total = n * (k + 3);
-        const int grid = (int)min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
         lean_unpack_simple_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t *>(rec), n, k, w0, w1, w2,
                                                        big_endian, sig, sig_is_u64, d_status);
     }
@@ -267,7 +269,7 @@ cudaError_t launch_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t see
 cudaError_t launch_band_keys_be(const uint32_t *sig, int64_t n, int k, int b, int r, uint8_t *out, int sm_count,
                                 cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    const int grid = (int)min<int64_t>((n + 7) / 8, (int64_t)sm_count * 8);
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count * 8);
     band_keys_be_kernel<<<grid, 256, 0, s>>>(sig, n, k, b * r, reinterpret_cast<uint2 *>(out));
     return cudaGetLastError();
 }
@@ -276,7 +278,7 @@ cudaError_t launch_band_fingerprints(const uint32_t *sig, int64_t n, int k, int 
                                      cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const int64_t total = n * b;
-    const int grid = (int)min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
     band_fingerprint_kernel<<<grid, 256, 0, s>>>(sig, n, k, b, r, out);
     return cudaGetLastError();
 }

@@ -281,6 +281,88 @@ int dsk_sig_merge_min(const uint32_t *d_x, const uint32_t *d_y, int64_t n_elems,
     return DSK_OK;
 }
 
+static int current_dev(DevInfo **dev) {
+    int device = 0;
+    DSK_CUDA(cudaGetDevice(&device));
+    return get_dev(device, dev);
+}
+
+int dsk_lean_pack(const void *d_sig, int sig_is_u64, int64_t n, int num_perm, int64_t seed, int big_endian,
+                  uint8_t *d_rec, void *stream) {
+    if (n < 0 || num_perm <= 0 || (n > 0 && (!d_sig || !d_rec))) {
+        set_error("dsk_lean_pack: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (((uintptr_t)d_rec & 3) != 0 || ((uintptr_t)d_sig & 3) != 0) {
+        set_error("dsk_lean_pack: buffers must be 4-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_lean_pack(d_sig, sig_is_u64, n, num_perm, seed, big_endian, d_rec, dev->sm_count,
+                              (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_lean_unpack(const uint8_t *d_rec, int64_t n, int num_perm, int64_t seed, int big_endian, void *d_sig,
+                    int sig_is_u64, int *d_status, void *stream) {
+    if (n < 0 || num_perm <= 0 || !d_status || (n > 0 && (!d_sig || !d_rec))) {
+        set_error("dsk_lean_unpack: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (((uintptr_t)d_rec & 3) != 0 || ((uintptr_t)d_sig & 3) != 0) {
+        set_error("dsk_lean_unpack: buffers must be 4-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_lean_unpack(d_rec, n, num_perm, seed, big_endian, d_sig, sig_is_u64, d_status, dev->sm_count,
+                                (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+static int check_bands(const char *who, int64_t n, int num_perm, int b, int r) {
+    if (n < 0 || num_perm <= 0 || b <= 0 || r <= 0 || (int64_t)b * r > num_perm) {
+        set_error("%s: need n >= 0, b, r > 0 and b*r <= num_perm (got b=%d r=%d num_perm=%d)", who, b, r, num_perm);
+        return DSK_ERR_INVALID;
+    }
+    return DSK_OK;
+}
+
+int dsk_band_keys(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint8_t *d_keys, void *stream) {
+    int rc = check_bands("dsk_band_keys", n, num_perm, b, r);
+    if (rc) return rc;
+    if (n > 0 && (!d_sig || !d_keys)) {
+        set_error("dsk_band_keys: null buffer");
+        return DSK_ERR_INVALID;
+    }
+    if (((uintptr_t)d_keys & 7) != 0) {
+        set_error("dsk_band_keys: d_keys must be 8-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    DevInfo *dev;
+    rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_band_keys_be(d_sig, n, num_perm, b, r, d_keys, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint64_t *d_fp, void *stream) {
+    int rc = check_bands("dsk_band_fingerprints", n, num_perm, b, r);
+    if (rc) return rc;
+    if (n > 0 && (!d_sig || !d_fp)) {
+        set_error("dsk_band_fingerprints: null buffer");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_band_fingerprints(d_sig, n, num_perm, b, r, d_fp, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

@@ -38,6 +38,15 @@ cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u6
 cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n, uint32_t *out, int sm_count,
                                  cudaStream_t s);
 
+cudaError_t launch_lean_pack(const void *sig, int sig_is_u64, int64_t n, int k, int64_t seed, int big_endian,
+                             uint8_t *rec, int sm_count, cudaStream_t s);
+cudaError_t launch_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t seed, int big_endian, void *sig,
+                               int sig_is_u64, int *d_status, int sm_count, cudaStream_t s);
+cudaError_t launch_band_keys_be(const uint32_t *sig, int64_t n, int k, int b, int r, uint8_t *out, int sm_count,
+                                cudaStream_t s);
+cudaError_t launch_band_fingerprints(const uint32_t *sig, int64_t n, int k, int b, int r, uint64_t *out, int sm_count,
+                                     cudaStream_t s);
+
 // ---- PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -25,6 +25,8 @@
 //   the min is < 7, where L'-7 would wrap) a slow exact pass over candidate blocks runs.
 // DIRECT kernel: the full 3.5-instruction evaluation for every (token, perm).
 // EXACT kernel: true 64-bit `% p` for every evaluation (any permutation, u32 or u64 tokens).
+#include <stdlib.h>
+
 #include "dsk_common.cuh"
 
 namespace dsk {
@@ -83,8 +85,8 @@ template <> struct TokLoad<uint64_t> {
     }
 };
 
-template <int P, int MODE, typename TokT>
-__global__ void __launch_bounds__(kWarps * 32) minhash_bulk_kernel(const BulkParams prm) {
+template <int P, int MODE, typename TokT, int OCC>
+__global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const BulkParams prm) {
     static_assert(MODE == MODE_EXACT || sizeof(TokT) == 4, "fast paths need 32-bit token hashes");
     constexpr int kBlkBytes = kBlkTok * (int)sizeof(TokT);
     constexpr int kBlkPerChunk = kChunkBytes / kBlkBytes;
@@ -423,24 +425,43 @@ __global__ void sig_merge_min_kernel(const uint32_t *__restrict__ x, const uint3
 }
 
 // ---- launchers --------------------------------------------------------------------------------
-template <int P, int MODE, typename TokT>
+template <int P, int MODE, typename TokT, int OCC>
 static cudaError_t launch_bulk(const BulkParams &prm, int sm_count, cudaStream_t s) {
     const int slices = (prm.k + 32 * P - 1) / (32 * P);
     int64_t gx = (prm.n_docs + kWarps - 1) / kWarps;
-    const int64_t gmax = (int64_t)sm_count * 4;
+    const int64_t gmax = (int64_t)sm_count * OCC;  // persistent: every CTA resident, one wave
     if (gx > gmax) gx = gmax;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    minhash_bulk_kernel<P, MODE, TokT><<<grid, kWarps * 32, 0, s>>>(prm);
+    minhash_bulk_kernel<P, MODE, TokT, OCC><<<grid, kWarps * 32, 0, s>>>(prm);
     return cudaGetLastError();
+}
+
+// CTAs per SM the two-phase kernel is compiled for (register cap = 65536 / (128 * OCC)).
+static int two_phase_occ() {
+    static int occ = [] {
+        const char *e = getenv("DSK_TWO_PHASE_OCC");
+        const int v = e ? atoi(e) : 4;
+        return (v == 4 || v == 5 || v == 6) ? v : 4;
+    }();
+    return occ;
 }
 
 template <int MODE, typename TokT>
 static cudaError_t launch_bulk_p(const BulkParams &prm, int sm_count, cudaStream_t s) {
-    if (prm.k <= 32) return launch_bulk<1, MODE, TokT>(prm, sm_count, s);
-    if (prm.k <= 64) return launch_bulk<2, MODE, TokT>(prm, sm_count, s);
-    if (prm.k <= 128) return launch_bulk<4, MODE, TokT>(prm, sm_count, s);
-    return launch_bulk<8, MODE, TokT>(prm, sm_count, s);
+    if (prm.k <= 32) return launch_bulk<1, MODE, TokT, 4>(prm, sm_count, s);
+    if (prm.k <= 64) return launch_bulk<2, MODE, TokT, 4>(prm, sm_count, s);
+    if (prm.k <= 128) {
+        if (MODE == MODE_TWO_PHASE) {
+            switch (two_phase_occ()) {
+                case 6: return launch_bulk<4, MODE, TokT, 6>(prm, sm_count, s);
+                case 5: return launch_bulk<4, MODE, TokT, 5>(prm, sm_count, s);
+                default: return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);
+            }
+        }
+        return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);
+    }
+    return launch_bulk<8, MODE, TokT, 3>(prm, sm_count, s);
 }
 
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s) {

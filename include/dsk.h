@@ -107,6 +107,29 @@ DSK_API int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, in
  * datasketch/minhash.py:359, :453; LeanMinHash.union lean_minhash.py:249). */
 DSK_API int dsk_sig_merge_min(const uint32_t *d_x, const uint32_t *d_y, int64_t n_elems, uint32_t *d_out, void *stream);
 
+/* ---- signature codecs (HBM-bound) ---------------------------------------------------
+ * LeanMinHash records: `struct` layout "<bo> q i {K}I" = seed int64, K int32, K x uint32
+ * (datasketch/lean_minhash.py:174-175 serialize, :201-214 deserialize, :216-232 pickle
+ * state).  big_endian = 0 for byteorder '<' '=' '@' (x86-64: 12 + 4K bytes, no padding),
+ * 1 for '>' '!'.  d_rec is [n, 12 + 4K] bytes.  Unpack validates every header against
+ * (seed, K) and sets *d_status = 1 on a mismatch (d_status must be zeroed by the caller). */
+DSK_API int dsk_lean_pack(const void *d_sig, int sig_is_u64, int64_t n, int num_perm, int64_t seed, int big_endian,
+                          uint8_t *d_rec, void *stream);
+DSK_API int dsk_lean_unpack(const uint8_t *d_rec, int64_t n, int num_perm, int64_t seed, int big_endian, void *d_sig,
+                            int sig_is_u64, int *d_status, void *stream);
+
+/* MinHashLSH band keys: for document i and band j, the r hash values
+ * sig[i][j*r:(j+1)*r] as big-endian uint64 -- byte-identical to the reference's default
+ * `_H` = bytes(hashvalues[start:end].byteswap().data) (datasketch/lsh.py:344, :427, :537-538).
+ * d_keys is [n, b, 8*r] bytes. */
+DSK_API int dsk_band_keys(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint8_t *d_keys, void *stream);
+
+/* 64-bit fingerprint of each band's r-tuple, [n, b] uint64: the bucket key of the GPU LSH
+ * index (equal tuples <=> equal fingerprints up to hash collisions, which the LSH kernels
+ * resolve by comparing the tuples themselves). */
+DSK_API int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint64_t *d_fp,
+                                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif
