@@ -12,7 +12,13 @@ _native.load()  # fail loudly if the CUDA library is absent
 from .hashfunc import sha1_hash32, sha1_hash64  # noqa: E402
 from .minhash import MinHash  # noqa: E402
 from .lean_minhash import LeanMinHash  # noqa: E402
+from .weighted_minhash import WeightedMinHash, WeightedMinHashGenerator  # noqa: E402
+from .lsh import GpuLSH, MinHashLSH, MinHashLSHDeletionSession, MinHashLSHInsertionSession  # noqa: E402
 from . import codec, engine  # noqa: E402
 
+# alias kept by the reference (datasketch/__init__.py:24-25)
+WeightedMinHashLSH = MinHashLSH
+
 __version__ = "0.1.0"
-__all__ = ["MinHash", "LeanMinHash", "sha1_hash32", "sha1_hash64", "engine", "codec"]
+__all__ = ["MinHash", "LeanMinHash", "WeightedMinHash", "WeightedMinHashGenerator", "MinHashLSH", "GpuLSH",
+           "WeightedMinHashLSH", "MinHashLSHInsertionSession", "MinHashLSHDeletionSession", "sha1_hash32", "sha1_hash64", "engine", "codec"]

@@ -41,6 +41,16 @@ SIGNATURES = {
     "dsk_minhash_bulk_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_void_p, c_int, c_int]),
     "dsk_sig_merge_min": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dsk_wmh_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "dsk_wmh_destroy": (None, [c_void_p]),
+    "dsk_wmh_minhash": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dsk_lsh_create": (c_int, [c_int, c_int, c_int, c_int64, c_int, ctypes.POINTER(c_void_p)]),
+    "dsk_lsh_destroy": (None, [c_void_p]),
+    "dsk_lsh_size": (c_int, [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "dsk_lsh_insert": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dsk_lsh_query_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dsk_lsh_query_fill": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dsk_exclusive_scan": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dsk_lean_pack": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "dsk_lean_unpack": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dsk_band_keys": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -107,6 +107,17 @@ struct dsk_perm {
     std::vector<uint64_t> a, b;
 };
 
+struct dsk_wmh {
+    int device = 0, ss = 0, ss_pad = 0, dim = 0;
+    float *d_par = nullptr;  // rs_t | lncs_t | betas_t, each [dim][ss_pad]
+};
+
+struct dsk_lsh {
+    int device = 0;
+    LshDev dev{};
+    int64_t n_docs = 0;
+};
+
 extern "C" {
 
 int dsk_version(void) { return DSK_VERSION; }
@@ -360,6 +371,182 @@ int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm, int b,
     rc = current_dev(&dev);
     if (rc) return rc;
     DSK_CUDA(launch_band_fingerprints(d_sig, n, num_perm, b, r, d_fp, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_wmh_create(const float *h_rs, const float *h_ln_cs, const float *h_betas, int sample_size, int dim, int device,
+                   dsk_wmh **out) {
+    if (!h_rs || !h_ln_cs || !h_betas || !out || sample_size <= 0 || dim <= 0) {
+        set_error("dsk_wmh_create: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *d;
+    int rc = get_dev(device, &d);
+    if (rc) return rc;
+    dsk_wmh *g = new (std::nothrow) dsk_wmh();
+    if (!g) return DSK_ERR_NOMEM;
+    g->device = device; g->ss = sample_size; g->dim = dim; g->ss_pad = (sample_size + 31) / 32 * 32;
+    const size_t plane = (size_t)dim * g->ss_pad, src_elems = (size_t)sample_size * dim;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    float *tmp = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_par, 3 * plane * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, src_elems * sizeof(float));
+    const float *srcs[3] = {h_rs, h_ln_cs, h_betas};
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+        e = cudaMemcpy(tmp, srcs[i], src_elems * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = launch_wmh_transpose(tmp, sample_size, dim, g->ss_pad, g->d_par + i * plane, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    }
+    if (tmp) cudaFree(tmp);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        if (g->d_par) cudaFree(g->d_par);
+        delete g;
+        return cuda_fail(e, "dsk_wmh_create");
+    }
+    *out = g;
+    return DSK_OK;
+}
+
+void dsk_wmh_destroy(dsk_wmh *g) {
+    if (!g) return;
+    if (g->d_par) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(g->device);
+        cudaFree(g->d_par);
+        cudaSetDevice(prev);
+    }
+    delete g;
+}
+
+int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_out, int32_t *d_status, void *stream) {
+    if (!g || n < 0 || (n > 0 && (!d_v || !d_out || !d_status))) {
+        set_error("dsk_wmh_minhash: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = get_dev(g->device, &dev);
+    if (rc) return rc;
+    const size_t plane = (size_t)g->dim * g->ss_pad;
+    DSK_CUDA(launch_wmh(g->d_par, g->d_par + plane, g->d_par + 2 * plane, g->ss, g->ss_pad, g->dim, d_v, n, d_out,
+                        d_status, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_lsh_create(int num_perm, int b, int r, int64_t capacity_docs, int device, dsk_lsh **out) {
+    int rc = check_bands("dsk_lsh_create", capacity_docs, num_perm, b, r);
+    if (rc) return rc;
+    if (!out || capacity_docs <= 0 || capacity_docs >= (1ll << 31)) {
+        set_error("dsk_lsh_create: capacity_docs must be in [1, 2^31)");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *d;
+    rc = get_dev(device, &d);
+    if (rc) return rc;
+    dsk_lsh *ix = new (std::nothrow) dsk_lsh();
+    if (!ix) return DSK_ERR_NOMEM;
+    ix->device = device;
+    LshDev &v = ix->dev;
+    v.k = num_perm; v.b = b; v.r = r; v.cap_docs = capacity_docs;
+    v.cap_slots = 1024;
+    while (v.cap_slots < 2 * capacity_docs) v.cap_slots <<= 1;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    const size_t slots = (size_t)b * v.cap_slots;
+    if (e == cudaSuccess) e = cudaMalloc(&v.sig, (size_t)capacity_docs * num_perm * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&v.slot_key, slots * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&v.slot_head, slots * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&v.next, (size_t)b * capacity_docs * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(v.slot_key, 0xFF, slots * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemset(v.slot_head, 0xFF, slots * sizeof(int32_t));
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        int rc2 = cuda_fail(e, "dsk_lsh_create");
+        dsk_lsh_destroy(ix);
+        return rc2;
+    }
+    *out = ix;
+    return DSK_OK;
+}
+
+void dsk_lsh_destroy(dsk_lsh *ix) {
+    if (!ix) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ix->device);
+    if (ix->dev.sig) cudaFree(ix->dev.sig);
+    if (ix->dev.slot_key) cudaFree(ix->dev.slot_key);
+    if (ix->dev.slot_head) cudaFree(ix->dev.slot_head);
+    if (ix->dev.next) cudaFree(ix->dev.next);
+    cudaSetDevice(prev);
+    delete ix;
+}
+
+int dsk_lsh_size(const dsk_lsh *ix, int64_t *n_docs, int64_t *capacity_docs) {
+    if (!ix) {
+        set_error("dsk_lsh_size: null handle");
+        return DSK_ERR_INVALID;
+    }
+    if (n_docs) *n_docs = ix->n_docs;
+    if (capacity_docs) *capacity_docs = ix->dev.cap_docs;
+    return DSK_OK;
+}
+
+int dsk_lsh_insert(dsk_lsh *ix, const uint32_t *d_sig, int64_t n, void *stream) {
+    if (!ix || n < 0 || (n > 0 && !d_sig)) {
+        set_error("dsk_lsh_insert: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (ix->n_docs + n > ix->dev.cap_docs) {
+        set_error("dsk_lsh_insert: capacity exceeded (%lld + %lld > %lld)", (long long)ix->n_docs, (long long)n,
+                  (long long)ix->dev.cap_docs);
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = get_dev(ix->device, &dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_lsh_insert(ix->dev, d_sig, ix->n_docs, n, dev->sm_count, (cudaStream_t)stream));
+    ix->n_docs += n;
+    return DSK_OK;
+}
+
+int dsk_lsh_query_count(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, int64_t *d_counts, void *stream) {
+    if (!ix || nq < 0 || (nq > 0 && (!d_qsig || !d_counts))) {
+        set_error("dsk_lsh_query_count: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = get_dev(ix->device, &dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_lsh_query(ix->dev, d_qsig, nq, ix->n_docs, d_counts, nullptr, nullptr, 0, dev->sm_count,
+                              (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_lsh_query_fill(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, const int64_t *d_ptr, int32_t *d_idx,
+                       void *stream) {
+    if (!ix || nq < 0 || (nq > 0 && (!d_qsig || !d_ptr))) {
+        set_error("dsk_lsh_query_fill: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = get_dev(ix->device, &dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_lsh_query(ix->dev, d_qsig, nq, ix->n_docs, nullptr, d_ptr, d_idx, 1, dev->sm_count,
+                              (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_exclusive_scan(const int64_t *d_in, int64_t n, int64_t *d_out, int64_t *d_scratch, void *stream) {
+    if (n < 0 || !d_out || (n > 0 && (!d_in || !d_scratch))) {
+        set_error("dsk_exclusive_scan: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    DSK_CUDA(launch_exclusive_scan(d_in, n, d_out, d_scratch, (cudaStream_t)stream));
     return DSK_OK;
 }
 

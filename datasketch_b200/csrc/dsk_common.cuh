@@ -47,6 +47,25 @@ cudaError_t launch_band_keys_be(const uint32_t *sig, int64_t n, int k, int b, in
 cudaError_t launch_band_fingerprints(const uint32_t *sig, int64_t n, int k, int b, int r, uint64_t *out, int sm_count,
                                      cudaStream_t s);
 
+cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, float *dst, cudaStream_t s);
+cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *betas_t, int ss, int ss_pad, int dim,
+                       const float *v, int64_t n, int64_t *out, int32_t *status, int sm_count, cudaStream_t s);
+
+// ---- device-resident LSH index (lsh_kernels.cu) -------------------------------------------------
+struct LshDev {
+    uint32_t *sig;        // [cap_docs][k] copies of the inserted signatures (tuple verification)
+    uint64_t *slot_key;   // [b][cap_slots]
+    int32_t *slot_head;   // [b][cap_slots]  most recently inserted doc of the bucket, -1 = none
+    int32_t *next;        // [b][cap_docs]   next doc in the same bucket, -1 = end
+    int64_t cap_docs, cap_slots;  // cap_slots is a power of two >= 2 * cap_docs
+    int k, b, r;
+};
+cudaError_t launch_lsh_insert(const LshDev &ix, const uint32_t *new_sig, int64_t doc0, int64_t n_new, int sm_count,
+                              cudaStream_t s);
+cudaError_t launch_lsh_query(const LshDev &ix, const uint32_t *qsig, int64_t nq, int64_t n_docs, int64_t *counts,
+                             const int64_t *ptr, int32_t *out, int fill, int sm_count, cudaStream_t s);
+cudaError_t launch_exclusive_scan(const int64_t *in, int64_t n, int64_t *out, int64_t *scratch, cudaStream_t s);
+
 // ---- PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -1,0 +1,197 @@
+// lsh_kernels.cu -- device-resident MinHashLSH index (sm_100a).
+//
+// Replaces the per-document Python work of MinHashLSH._insert / query
+// (datasketch/lsh.py:326-347, :370-432 over dict storage, storage.py:209-259):
+//   insert: for each band j, bucket[j][ _H(sig[j*r:(j+1)*r]) ].add(doc)
+//   query : union over bands of bucket[j][ _H(qsig[j*r:(j+1)*r]) ]
+// The reference's bucket key is the r-tuple itself (`_H` = byteswap, lsh.py:537-538), so two
+// documents share a bucket iff their r-tuples are EQUAL.  Here a bucket is found through a 64-bit
+// fingerprint of the tuple in a per-band open-addressing table (atomicCAS claim), members are
+// chained through next[band][doc] (atomicExch on the bucket head), and every candidate is verified
+// by comparing the r-tuple itself, so the candidate sets are exactly the reference's.
+// A candidate that matches in several bands is emitted once (by the first matching band), which is
+// the set-union of lsh.py:426-429.
+#include "dsk_common.cuh"
+
+namespace dsk {
+
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ uint64_t lsh_mix64(uint64_t h) {
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    return h;
+}
+
+__device__ __forceinline__ uint64_t band_fp(const uint32_t *v, int r, int band) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)band;
+    for (int q = 0; q < r; ++q) h = (h ^ v[q]) * 0xFF51AFD7ED558CCDull + 0x2545F4914F6CDD1Dull;
+    h = lsh_mix64(h);
+    return h == kEmptyKey ? h - 1 : h;
+}
+
+__device__ __forceinline__ bool tuple_eq(const uint32_t *a, const uint32_t *b, int r) {
+    bool eq = true;
+    for (int q = 0; q < r; ++q) eq = eq && (a[q] == b[q]);
+    return eq;
+}
+
+// thread <-> (new document, band)
+__global__ void __launch_bounds__(256) lsh_insert_kernel(const LshDev ix, const uint32_t *__restrict__ new_sig,
+                                                         int64_t doc0, int64_t n_new) {
+    const int64_t total = n_new * ix.b, stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t mask = (uint64_t)ix.cap_slots - 1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t i = e / ix.b;
+        const int band = (int)(e - i * ix.b);
+        const int64_t doc = doc0 + i;
+        const uint32_t *row = new_sig + i * ix.k;
+        const uint64_t fp = band_fp(row + (int64_t)band * ix.r, ix.r, band);
+        uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
+        uint64_t slot = lsh_mix64(fp) & mask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(keys + slot),
+                                                      (unsigned long long)kEmptyKey, (unsigned long long)fp);
+            if (prev == kEmptyKey || prev == fp) break;
+            slot = (slot + 1) & mask;
+        }
+        const int32_t old = atomicExch(ix.slot_head + (int64_t)band * ix.cap_slots + slot, (int32_t)doc);
+        ix.next[(int64_t)band * ix.cap_docs + doc] = old;
+    }
+}
+
+// warp <-> query, lane <-> band (bands beyond 32 are handled in further rounds).
+// FILL = false: counts[q] = number of distinct candidates.  FILL = true: writes them at out[ptr[q]...].
+template <bool FILL>
+__global__ void __launch_bounds__(256) lsh_query_kernel(const LshDev ix, const uint32_t *__restrict__ qsig, int64_t nq,
+                                                        int64_t n_docs, int64_t *__restrict__ counts,
+                                                        const int64_t *__restrict__ ptr, int32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t mask = (uint64_t)ix.cap_slots - 1;
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += warps) {
+        const uint32_t *qrow = qsig + q * ix.k;
+        int64_t base = FILL ? ptr[q] : 0;
+        int64_t total = 0;
+        for (int band0 = 0; band0 < ix.b; band0 += 32) {
+            const int band = band0 + lane;
+            // pass 0 counts this lane's distinct candidates, pass 1 (FILL) writes them after a warp scan
+            int mine = 0;
+            int64_t wpos = 0;
+            for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
+                int cnt = 0;
+                if (band < ix.b) {
+                    const uint32_t *qt = qrow + (int64_t)band * ix.r;
+                    const uint64_t fp = band_fp(qt, ix.r, band);
+                    const uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
+                    uint64_t slot = lsh_mix64(fp) & mask;
+                    int32_t d = -1;
+                    while (true) {
+                        const uint64_t kk = keys[slot];
+                        if (kk == fp) { d = ix.slot_head[(int64_t)band * ix.cap_slots + slot]; break; }
+                        if (kk == kEmptyKey) break;
+                        slot = (slot + 1) & mask;
+                    }
+                    while (d >= 0) {
+                        if (d < n_docs) {
+                            const uint32_t *drow = ix.sig + (int64_t)d * ix.k;
+                            if (tuple_eq(drow + (int64_t)band * ix.r, qt, ix.r)) {
+                                bool dup = false;  // already produced by an earlier band?
+                                for (int j = 0; j < band && !dup; ++j)
+                                    dup = tuple_eq(drow + (int64_t)j * ix.r, qrow + (int64_t)j * ix.r, ix.r);
+                                if (!dup) {
+                                    if (FILL && pass == 1) out[wpos + cnt] = d;
+                                    ++cnt;
+                                }
+                            }
+                        }
+                        d = ix.next[(int64_t)band * ix.cap_docs + d];
+                    }
+                }
+                if (pass == 0) {
+                    mine = cnt;
+                    int incl = mine;  // inclusive warp scan of per-lane counts
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    wpos = base + total + (incl - mine);
+                    total += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
+            }
+        }
+        if (!FILL && lane == 0) counts[q] = total;
+    }
+}
+
+// ---- exclusive scan of int64 counts (three small kernels) -------------------------------------------
+constexpr int kScanBlock = 1024;
+
+__global__ void __launch_bounds__(kScanBlock) scan_block_kernel(const int64_t *in, int64_t n, int64_t *out,
+                                                                int64_t *block_sums) {
+    __shared__ int64_t s[kScanBlock];
+    const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    const int64_t v = i < n ? in[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+        const int64_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (i < n) out[i] = s[threadIdx.x] - v;  // exclusive
+    if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = s[threadIdx.x];
+}
+
+__global__ void scan_sums_kernel(int64_t *block_sums, int64_t nb) {  // single thread block, serial over blocks
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int64_t run = 0;
+        for (int64_t i = 0; i < nb; ++i) { const int64_t t = block_sums[i]; block_sums[i] = run; run += t; }
+        block_sums[nb] = run;
+    }
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_add_kernel(int64_t *out, int64_t n, const int64_t *block_sums,
+                                                              int64_t nb) {
+    const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    if (i < n) out[i] += block_sums[blockIdx.x];
+    if (i == 0) out[n] = block_sums[nb];  // total
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+cudaError_t launch_lsh_insert(const LshDev &ix, const uint32_t *new_sig, int64_t doc0, int64_t n_new, int sm_count,
+                              cudaStream_t s) {
+    if (n_new <= 0) return cudaSuccess;
+    // the index keeps its own copy of the rows: candidates are verified on the r-tuples themselves
+    cudaError_t e = cudaMemcpyAsync(ix.sig + doc0 * ix.k, new_sig, (size_t)n_new * ix.k * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+    const int64_t total = n_new * ix.b;
+    int64_t grid = (total + 255) / 256;
+    if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
+    lsh_insert_kernel<<<(unsigned)grid, 256, 0, s>>>(ix, new_sig, doc0, n_new);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lsh_query(const LshDev &ix, const uint32_t *qsig, int64_t nq, int64_t n_docs, int64_t *counts,
+                             const int64_t *ptr, int32_t *out, int fill, int sm_count, cudaStream_t s) {
+    if (nq <= 0) return cudaSuccess;
+    int64_t grid = (nq + 7) / 8;
+    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+    if (fill) lsh_query_kernel<true><<<(unsigned)grid, 256, 0, s>>>(ix, qsig, nq, n_docs, counts, ptr, out);
+    else lsh_query_kernel<false><<<(unsigned)grid, 256, 0, s>>>(ix, qsig, nq, n_docs, counts, ptr, out);
+    return cudaGetLastError();
+}
+
+// out has n + 1 entries; scratch needs (n / 1024 + 2) int64
+cudaError_t launch_exclusive_scan(const int64_t *in, int64_t n, int64_t *out, int64_t *scratch, cudaStream_t s) {
+    const int64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    if (n <= 0) return cudaMemsetAsync(out, 0, sizeof(int64_t), s);
+    scan_block_kernel<<<(unsigned)nb, kScanBlock, 0, s>>>(in, n, out, scratch);
+    scan_sums_kernel<<<1, 32, 0, s>>>(scratch, nb);
+    scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, s>>>(out, n, scratch, nb);
+    return cudaGetLastError();
+}
+
+}  // namespace dsk

@@ -1,0 +1,144 @@
+"""Weighted MinHash with the reference's API (datasketch/weighted_minhash.py:11-159).
+
+``WeightedMinHashGenerator.__init__`` draws the ICWS parameters on the host with numpy,
+bit-identically to the reference (:118-121).  ``minhash`` (one vector) and
+``minhash_batch`` (a matrix) run the per-sample argmin in ``libdsk_b200.so``
+(``dsk_wmh_minhash``); every float32 step after ``log`` is IEEE-identical to numpy.
+"""
+from __future__ import annotations
+
+import collections.abc
+import copy
+import ctypes
+from typing import List
+
+import numpy as np
+
+from . import _native as nv
+
+
+class WeightedMinHash:
+    """Container produced by :class:`WeightedMinHashGenerator` (weighted_minhash.py:11-95)."""
+
+    def __init__(self, seed: int, hashvalues: np.ndarray) -> None:
+        self.seed = seed
+        self.hashvalues = hashvalues
+
+    def jaccard(self, other: "WeightedMinHash") -> float:
+        """Fraction of samples whose (k, t) rows agree (weighted_minhash.py:28-60)."""
+        if other.seed != self.seed:
+            raise ValueError("Cannot compute Jaccard given WeightedMinHash objects with different seeds")
+        if len(self) != len(other):
+            raise ValueError("Cannot compute Jaccard given WeightedMinHash objects with different numbers of "
+                             "hash values")
+        same = np.all(np.asarray(self.hashvalues) == np.asarray(other.hashvalues), axis=1)
+        return float(np.count_nonzero(same)) / float(len(self))
+
+    def digest(self) -> np.ndarray:
+        return copy.copy(self.hashvalues)
+
+    def copy(self) -> "WeightedMinHash":
+        return WeightedMinHash(self.seed, self.digest())
+
+    def __len__(self) -> int:
+        return len(self.hashvalues)
+
+    def __eq__(self, other) -> bool:
+        return (type(self) is type(other) and self.seed == other.seed
+                and np.array_equal(self.hashvalues, other.hashvalues))
+
+    __hash__ = None
+
+
+class WeightedMinHashGenerator:
+    """Creates :class:`WeightedMinHash` objects (weighted_minhash.py:98-159)."""
+
+    def __init__(self, dim: int, sample_size: int = 128, seed: int = 1) -> None:
+        self.dim = dim
+        self.sample_size = sample_size
+        self.seed = seed
+        generator = np.random.RandomState(seed=seed)
+        # drawn in exactly this order from one RandomState (weighted_minhash.py:118-121)
+        self.rs = generator.gamma(2, 1, (sample_size, dim)).astype(np.float32)
+        self.ln_cs = np.log(generator.gamma(2, 1, (sample_size, dim))).astype(np.float32)
+        self.betas = generator.uniform(0, 1, (sample_size, dim)).astype(np.float32)
+        self._handles = {}
+
+    # -- device state (dropped on pickling) -----------------------------------------------------
+    def _handle(self, device: int = 0):
+        h = self._handles.get(device)
+        if h is None:
+            nv.require_device(device)
+            ptr = ctypes.c_void_p()
+            rs, lc, be = (np.ascontiguousarray(x, dtype=np.float32) for x in (self.rs, self.ln_cs, self.betas))
+            nv.check(nv.load().dsk_wmh_create(rs.ctypes.data, lc.ctypes.data, be.ctypes.data, self.sample_size,
+                                              self.dim, device, ctypes.byref(ptr)))
+            h = ptr
+            self._handles[device] = h
+        return h
+
+    def __del__(self):
+        try:
+            for h in getattr(self, "_handles", {}).values():
+                nv.load().dsk_wmh_destroy(h)
+            self._handles = {}
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_handles"] = {}
+        return st
+
+    # -- sampling ----------------------------------------------------------------------------------
+    def minhash_batch(self, X, device: int = 0) -> np.ndarray:
+        """[n, dim] weights -> [n, sample_size, 2] int64 of (k, t) -- row i equals
+        ``self.minhash(X[i]).hashvalues``.  Raises ValueError if any row is all zeros."""
+        import torch
+        if isinstance(X, np.ndarray):
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            if X.ndim != 2 or X.shape[1] != self.dim:
+                raise ValueError("Input dimension mismatch, expecting %d" % self.dim)
+            h = self._handle(device)
+            d_v = torch.from_numpy(X).cuda(device)
+        else:
+            if X.dim() != 2 or X.shape[1] != self.dim:
+                raise ValueError("Input dimension mismatch, expecting %d" % self.dim)
+            d_v = X.to(dtype=torch.float32).contiguous()
+            device = d_v.device.index
+            h = self._handle(device)
+        n = d_v.shape[0]
+        d_out = torch.empty((n, self.sample_size, 2), dtype=torch.int64, device=d_v.device)
+        d_st = torch.empty((n,), dtype=torch.int32, device=d_v.device)
+        with torch.cuda.device(device):
+            nv.check(nv.load().dsk_wmh_minhash(h, d_v.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(),
+                                               torch.cuda.current_stream(d_v.device).cuda_stream))
+        if n and bool(d_st.any().item()):
+            raise ValueError("Input is all zeros")
+        return d_out.cpu().numpy()
+
+    def minhash(self, v) -> WeightedMinHash:
+        """One weighted Jaccard vector -> WeightedMinHash (weighted_minhash.py:123-159; same checks)."""
+        if not isinstance(v, collections.abc.Sized):
+            raise TypeError("Input vector must be sized")
+        if not len(v) == self.dim:
+            raise ValueError("Input dimension mismatch, expecting %d" % self.dim)
+        v = np.array(v, dtype=np.float32)  # a private float32 copy: the input is never mutated
+        if not (v != 0).any():
+            raise ValueError("Input is all zeros")
+        out = self.minhash_batch(v.reshape(1, -1))
+        return WeightedMinHash(self.seed, out[0].astype(int, copy=False))
+
+    def minhash_many(self, X) -> List[WeightedMinHash]:
+        """Batch convenience: one WeightedMinHash per row, each equal to ``minhash(row)``.
+
+        Note: the reference's experimental ``minhash_many`` (weighted_minhash.py:161-247) uses a
+        different sampling formula and returns different values than ``minhash``; it is outside
+        this engine's scope.  Here every row follows ``minhash`` exactly."""
+        if hasattr(X, "toarray"):
+            X = X.toarray()
+        X = np.asarray(X)
+        if X.ndim == 1:
+            X = X.reshape(1, -1)
+        out = self.minhash_batch(X)
+        return [WeightedMinHash(self.seed, row.astype(int, copy=False)) for row in out]

@@ -130,6 +130,42 @@ DSK_API int dsk_band_keys(const uint32_t *d_sig, int64_t n, int num_perm, int b,
 DSK_API int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint64_t *d_fp,
                                   void *stream);
 
+/* ---- Weighted MinHash (Ioffe ICWS) ------------------------------------------------------
+ * Handle = device copy of the generator parameters rs, ln_cs, betas, each [sample_size, dim]
+ * float32, drawn on the HOST by numpy exactly as WeightedMinHashGenerator.__init__ does
+ * (datasketch/weighted_minhash.py:118-121).  dsk_wmh_minhash replaces the per-sample loop
+ * of WeightedMinHashGenerator.minhash (:147-158) for a batch of n vectors:
+ *   d_v      [n, dim] float32 weights (zeros are skipped, :148-152)
+ *   d_out    [n, sample_size, 2] int64: (k, int(t_k)) per sample (:158)
+ *   d_status [n] int32: 1 where the input row is all zeros (reference: ValueError, :149-150) */
+typedef struct dsk_wmh dsk_wmh;
+DSK_API int dsk_wmh_create(const float *h_rs, const float *h_ln_cs, const float *h_betas, int sample_size, int dim,
+                           int device, dsk_wmh **out);
+DSK_API void dsk_wmh_destroy(dsk_wmh *g);
+DSK_API int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_out, int32_t *d_status,
+                            void *stream);
+
+/* ---- device-resident MinHashLSH index ------------------------------------------------------
+ * Replaces the bucket step of MinHashLSH._insert / query over dict storage
+ * (datasketch/lsh.py:344-347, :426-429; storage.py:209-259) for whole batches.  Documents are
+ * numbered 0..n_docs-1 in insertion order (the host layer maps numbers to user keys).  Buckets
+ * are exact: two documents meet iff a band's r-tuple is equal, as with the reference's byte keys.
+ *   dsk_lsh_insert       append n signatures ([n, num_perm] u32) to the index
+ *   dsk_lsh_query_count  d_counts[q] = number of distinct candidates of query q
+ *   dsk_exclusive_scan   d_out[0..n] = exclusive prefix sums of d_in[0..n-1] (d_out[n] = total);
+ *                        d_scratch holds at least n/1024 + 2 int64
+ *   dsk_lsh_query_fill   writes each query's candidates (document numbers, unordered like the
+ *                        reference's list(set), lsh.py:432) at d_idx[d_ptr[q] .. d_ptr[q+1]) */
+typedef struct dsk_lsh dsk_lsh;
+DSK_API int dsk_lsh_create(int num_perm, int b, int r, int64_t capacity_docs, int device, dsk_lsh **out);
+DSK_API void dsk_lsh_destroy(dsk_lsh *ix);
+DSK_API int dsk_lsh_size(const dsk_lsh *ix, int64_t *n_docs, int64_t *capacity_docs);
+DSK_API int dsk_lsh_insert(dsk_lsh *ix, const uint32_t *d_sig, int64_t n, void *stream);
+DSK_API int dsk_lsh_query_count(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, int64_t *d_counts, void *stream);
+DSK_API int dsk_lsh_query_fill(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, const int64_t *d_ptr,
+                               int32_t *d_idx, void *stream);
+DSK_API int dsk_exclusive_scan(const int64_t *d_in, int64_t n, int64_t *d_out, int64_t *d_scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
