@@ -106,3 +106,26 @@ def band_fingerprints(sig, b: int, r: int, stream=None):
     with torch.cuda.device(d_sig.device):
         nv.check(nv.load().dsk_band_fingerprints(d_sig.data_ptr(), n, k, b, r, out.data_ptr(), _stream(d_sig, stream)))
     return out
+
+
+def jaccard_pairs(sig, i, j, stream=None):
+    """Jaccard estimates of the row pairs (i[p], j[p]) of one signature matrix: float64 array of
+    ``count_equal / K`` exactly as ``MinHash.jaccard`` (minhash.py:324) computes it."""
+    torch = _torch()
+    d_sig, is64 = _as_device_sig(sig)
+    if is64:
+        raise TypeError("jaccard_pairs takes the 32-bit signature matrix")
+    n, k = d_sig.shape
+    di = torch.as_tensor(np.asarray(i, dtype=np.int64) if not hasattr(i, "is_cuda") else i).to(d_sig.device).contiguous()
+    dj = torch.as_tensor(np.asarray(j, dtype=np.int64) if not hasattr(j, "is_cuda") else j).to(d_sig.device).contiguous()
+    if di.shape != dj.shape:
+        raise ValueError("pair index arrays differ in length")
+    m = di.numel()
+    out = torch.empty((max(m, 1),), dtype=torch.int32, device=d_sig.device)
+    with torch.cuda.device(d_sig.device):
+        nv.check(nv.load().dsk_jaccard_pairs(d_sig.data_ptr(), n, k, di.data_ptr(), dj.data_ptr(), m, out.data_ptr(),
+                                             _stream(d_sig, stream)))
+    cnt = out[:m].cpu().numpy()
+    if (cnt < 0).any():
+        raise IndexError("pair index out of range")
+    return cnt.astype(np.float64) / float(k)

@@ -550,6 +550,23 @@ int dsk_exclusive_scan(const int64_t *d_in, int64_t n, int64_t *d_out, int64_t *
     return DSK_OK;
 }
 
+int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_perm, const int64_t *d_i, const int64_t *d_j,
+                      int64_t m, int32_t *d_count, void *stream) {
+    if (n_rows < 0 || num_perm <= 0 || m < 0 || (m > 0 && (!d_sig || !d_i || !d_j || !d_count))) {
+        set_error("dsk_jaccard_pairs: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if ((num_perm & 3) == 0 && ((uintptr_t)d_sig & 15) != 0) {
+        set_error("dsk_jaccard_pairs: d_sig must be 16-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_jaccard_pairs(d_sig, n_rows, num_perm, d_i, d_j, m, d_count, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

@@ -166,6 +166,14 @@ DSK_API int dsk_lsh_query_fill(const dsk_lsh *ix, const uint32_t *d_qsig, int64_
                                int32_t *d_idx, void *stream);
 DSK_API int dsk_exclusive_scan(const int64_t *d_in, int64_t n, int64_t *d_out, int64_t *d_scratch, void *stream);
 
+/* ---- Jaccard estimate -----------------------------------------------------------------------
+ * d_count[p] = number of positions where rows d_i[p] and d_j[p] of the [n_rows, num_perm] u32
+ * signature matrix are equal; jaccard = count / num_perm (MinHash.jaccard,
+ * datasketch/minhash.py:324; seeds / lengths are validated by the host layer as :314-323).
+ * An out-of-range pair index yields -1. */
+DSK_API int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_perm, const int64_t *d_i,
+                              const int64_t *d_j, int64_t m, int32_t *d_count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,3 +111,25 @@ def test_band_keys_golden_and_fingerprints(dsk, golden):
         same_fp = fp[:60, j][:, None] == fp[:60, j][None, :]
         assert np.array_equal(same_key, same_fp)
     assert len(np.unique(fp)) > 0.5 * fp.size
+
+
+@pytest.mark.parametrize("k", [128, 100, 256, 4])
+def test_jaccard_pairs_vs_oracle(dsk, k):
+    rs = np.random.RandomState(k)
+    n, m = 5000, 20000
+    sig = rs.randint(0, 4, size=(n, k)).astype(np.uint32)     # low entropy: many equal positions
+    ia, ib = rs.randint(0, n, size=m), rs.randint(0, n, size=m)
+    ia[:10] = ib[:10]                                          # identical rows -> 1.0
+    got = dsk.codec.jaccard_pairs(sig, ia, ib)
+    want = oc.jaccard_pairs_u32(sig, ia, ib).astype(np.float64) / k
+    assert got.dtype == np.float64 and np.array_equal(got, want) and (got[:10] == 1.0).all()
+    for p in range(5):
+        assert got[p] == o.jaccard(sig[ia[p]].astype(np.uint64), sig[ib[p]].astype(np.uint64))
+    with pytest.raises(IndexError):
+        dsk.codec.jaccard_pairs(sig, [0, n], [1, 2])
+
+
+def test_jaccard_pairs_matches_golden_objects(dsk, golden):
+    g = golden("minhash")
+    sig = np.stack([g["j_m1"], g["j_m2"]]).astype(np.uint32)
+    assert dsk.codec.jaccard_pairs(sig, [0], [1])[0] == float(g["j_jaccard"])

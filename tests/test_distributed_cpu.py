@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (token-balanced document sharding and the
+all-gather that assembles the signature matrix).  The per-rank compute is injected (the oracle,
+as a checker stand-in) because this container has no GPU; the product default is the CUDA engine."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle_clib as oc
+from oracle import oracle_np as o
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tok, off, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datasketch_b200.distributed import shard_bounds, sharded_bulk_signatures
+    P = o.init_permutations(64, 5)
+
+    def compute(t, f, perms):
+        return torch.from_numpy(oc.minhash_bulk_u32tok(t, f, perms).view(np.int32).copy())
+
+    full, (d0, d1) = sharded_bulk_signatures(tok, off, P, compute=compute)
+    local, _ = sharded_bulk_signatures(tok, off, P, compute=compute, gather=False)
+    assert (d0, d1) == shard_bounds(off, world)[rank] and local.shape[0] == d1 - d0
+    ret[rank] = (full.numpy().view(np.uint32).copy(), d0, d1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_sharded_signatures_gloo_world2(ragged):
+    rs = np.random.RandomState(3)
+    n = 101
+    lens = rs.randint(0, 60, size=n) if ragged else np.full(n, 32)
+    if ragged:
+        lens[:40] = 0        # leading empty documents -> unbalanced document counts per shard
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 2 ** 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    want = oc.minhash_bulk_u32tok(tok, off, o.init_permutations(64, 5))
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), tok, off, ret), nprocs=2, join=True)
+    (f0, a0, b0), (f1, a1, b1) = ret[0], ret[1]
+    assert a0 == 0 and b0 == a1 and b1 == n
+    assert np.array_equal(f0, want) and np.array_equal(f1, want)
+
+
+def test_shard_bounds_properties():
+    from datasketch_b200.distributed import shard_bounds
+    rs = np.random.RandomState(0)
+    for world in (1, 2, 3, 8):
+        for _ in range(20):
+            n = rs.randint(0, 50)
+            off = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(rs.randint(0, 100, size=n), out=off[1:])
+            b = shard_bounds(off, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1)) and all(x <= y for x, y in b)
+            if n and off[-1] > 0:
+                per = [off[y] - off[x] for x, y in b]
+                assert max(per) <= off[-1] / world + np.diff(off).max()
