@@ -129,3 +129,29 @@ def jaccard_pairs(sig, i, j, stream=None):
     if (cnt < 0).any():
         raise IndexError("pair index out of range")
     return cnt.astype(np.float64) / float(k)
+
+
+def jaccard_topk(queries, db, topk: int = 10, self_base: int = -1, to_host: bool = True, stream=None):
+    """For every query row: the ``topk`` database rows with the highest Jaccard estimate
+    (count of equal positions / K), best first, ties -> lower index.  ``self_base >= 0`` means
+    query i *is* database row ``self_base + i`` and is left out of its own list.
+
+    Returns ``(jaccard float64 [Q, topk], index int64 [Q, topk])`` (index -1 where the database
+    has fewer than ``topk`` other rows)."""
+    torch = _torch()
+    d_q, q64 = _as_device_sig(queries)
+    d_db, db64 = _as_device_sig(db)
+    if q64 or db64:
+        raise TypeError("jaccard_topk takes 32-bit signature matrices")
+    if d_q.shape[1] != d_db.shape[1]:
+        raise ValueError("Cannot compute Jaccard given MinHash with different numbers of permutation functions")
+    nq, k = d_q.shape
+    cnt = torch.empty((nq, topk), dtype=torch.int32, device=d_q.device)
+    idx = torch.empty((nq, topk), dtype=torch.int64, device=d_q.device)
+    with torch.cuda.device(d_q.device):
+        nv.check(nv.load().dsk_jaccard_topk(d_q.data_ptr(), nq, d_db.data_ptr(), d_db.shape[0], k, topk, self_base,
+                                            cnt.data_ptr(), idx.data_ptr(), _stream(d_q, stream)))
+    if not to_host:
+        return cnt, idx
+    c = cnt.cpu().numpy()
+    return np.where(c >= 0, c, 0).astype(np.float64) / float(k), idx.cpu().numpy()

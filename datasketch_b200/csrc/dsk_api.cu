@@ -567,6 +567,25 @@ int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_perm, const
     return DSK_OK;
 }
 
+int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
+                     int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *stream) {
+    if (nq < 0 || n < 0 || num_perm <= 0 || num_perm > 4096 || topk <= 0 || topk > 32 ||
+        (nq > 0 && (!d_q || !d_cnt || !d_idx)) || (n > 0 && !d_db)) {
+        set_error("dsk_jaccard_topk: bad arguments (need 0 < topk <= 32, 0 < num_perm <= 4096)");
+        return DSK_ERR_INVALID;
+    }
+    if ((num_perm & 3) == 0 && ((uintptr_t)d_db & 15) != 0) {
+        set_error("dsk_jaccard_topk: d_db must be 16-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_jaccard_topk(d_q, nq, d_db, n, num_perm, topk, self_base, d_cnt, d_idx, dev->sm_count,
+                                 (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

@@ -69,6 +69,9 @@ cudaError_t launch_exclusive_scan(const int64_t *in, int64_t n, int64_t *out, in
 cudaError_t launch_jaccard_pairs(const uint32_t *sig, int64_t n_rows, int k, const int64_t *ia, const int64_t *ib,
                                  int64_t m, int32_t *out, int sm_count, cudaStream_t s);
 
+cudaError_t launch_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *db, int64_t n, int k, int topk,
+                                int64_t self_base, int32_t *out_cnt, int64_t *out_idx, int sm_count, cudaStream_t s);
+
 // ---- PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -174,6 +174,13 @@ DSK_API int dsk_exclusive_scan(const int64_t *d_in, int64_t n, int64_t *d_out, i
 DSK_API int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_perm, const int64_t *d_i,
                               const int64_t *d_j, int64_t m, int32_t *d_count, void *stream);
 
+/* All-pairs top-k: for each of nq query rows, the `topk` (<= 32) rows of the [n, num_perm]
+ * database with the most equal positions, best first; ties -> lower database index.  If
+ * self_base >= 0, query i is database row self_base + i and is excluded from its own list.
+ * d_cnt [nq, topk] int32 counts (jaccard = cnt / num_perm), d_idx [nq, topk] int64 (-1 pads). */
+DSK_API int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
+                             int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,3 +133,50 @@ def test_jaccard_pairs_matches_golden_objects(dsk, golden):
     g = golden("minhash")
     sig = np.stack([g["j_m1"], g["j_m2"]]).astype(np.uint32)
     assert dsk.codec.jaccard_pairs(sig, [0], [1])[0] == float(g["j_jaccard"])
+
+
+def _topk_oracle(q, db, topk, self_base):
+    out_c, out_i = [], []
+    for i, row in enumerate(q):
+        cnt = (db == row[None, :]).sum(axis=1).astype(np.int64)
+        order = np.lexsort((np.arange(len(db)), -cnt))          # count desc, index asc
+        if self_base >= 0:
+            order = order[order != self_base + i]
+        order = order[:topk]
+        c = np.full(topk, -1, np.int64); ix = np.full(topk, -1, np.int64)
+        c[:len(order)] = cnt[order]; ix[:len(order)] = order
+        out_c.append(c); out_i.append(ix)
+    return np.stack(out_c), np.stack(out_i)
+
+
+@pytest.mark.parametrize("k,n,nq,topk,self_base", [(128, 1000, 150, 10, 0), (100, 333, 70, 5, -1), (128, 7, 7, 10, 0),
+                                                    (64, 2000, 65, 32, 500), (256, 300, 10, 1, -1)])
+def test_jaccard_topk_vs_oracle(dsk, k, n, nq, topk, self_base):
+    rs = np.random.RandomState(n + k)
+    db = rs.randint(0, 3, size=(n, k)).astype(np.uint32)       # low entropy: many ties, large counts
+    db[rs.randint(0, n, 20)] = db[rs.randint(0, n, 20)]
+    if self_base >= 0:
+        q = db[self_base:self_base + nq].copy()
+        nq = len(q)
+    else:
+        q = rs.randint(0, 3, size=(nq, k)).astype(np.uint32)
+    jac, idx = dsk.codec.jaccard_topk(q, db, topk=topk, self_base=self_base)
+    wc, wi = _topk_oracle(q, db, topk, self_base)
+    assert np.array_equal(idx, wi)
+    assert np.array_equal(jac, np.where(wc >= 0, wc, 0) / float(k))
+
+
+def test_jaccard_topk_random_signatures_finds_planted_pairs(dsk):
+    # C5-shaped data, scaled: uniformly random signatures (all counts 0 -> ties by index) with planted near-duplicates
+    rs = np.random.RandomState(5)
+    n, k = 20_000, 128
+    db = rs.randint(0, 2 ** 32, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    for i in range(0, 2000, 2):
+        db[i + 1] = db[i]
+        db[i + 1, rs.choice(k, 10, replace=False)] = 7
+    q = db[:512]
+    jac, idx = dsk.codec.jaccard_topk(q, db, topk=10, self_base=0)
+    wc, wi = _topk_oracle(q[:64], db, 10, 0)
+    assert np.array_equal(idx[:64], wi)
+    assert all(idx[i, 0] == i + 1 for i in range(0, 512, 2)) and all(idx[i, 0] == i - 1 for i in range(1, 512, 2))
+    assert (jac[:, 0] >= 118 / 128).all() and (jac[:, 1] == 0).all()
