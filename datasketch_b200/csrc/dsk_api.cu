@@ -1,5 +1,6 @@
 // dsk_api.cu -- the C-ABI (include/dsk.h): argument validation, permutation analysis,
 // kernel selection, and the pipelined host-buffer entry point.
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string.h>
@@ -104,8 +105,14 @@ struct dsk_perm {
     int kpad = 0;
     int n_unsafe = 0;
     uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi, each kpad entries
+    unsigned *d_counters = nullptr;  // kCounterSets x kCounterStride work counters (one set per in-flight launch)
+    mutable std::atomic<unsigned> next_set{0};
     std::vector<uint64_t> a, b;
 };
+static constexpr int kCounterSets = 64, kCounterStride = 64;
+static unsigned *perm_counters(const dsk_perm *p) {
+    return p->d_counters + (size_t)(p->next_set.fetch_add(1) % kCounterSets) * kCounterStride;
+}
 
 struct dsk_wmh {
     int device = 0, ss = 0, ss_pad = 0, dim = 0;
@@ -145,8 +152,8 @@ int dsk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, siz
 }
 
 int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int device, dsk_perm **out) {
-    if (!h_a || !h_b || !out || num_perm <= 0) {
-        set_error("dsk_perm_create: bad arguments (num_perm=%d)", num_perm);
+    if (!h_a || !h_b || !out || num_perm <= 0 || num_perm > 256 * kCounterStride) {
+        set_error("dsk_perm_create: bad arguments (num_perm=%d; supported range 1..%d)", num_perm, 256 * kCounterStride);
         return DSK_ERR_INVALID;
     }
     DevInfo *d;
@@ -175,10 +182,12 @@ int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int 
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_tab, tab.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_counters, sizeof(unsigned) * kCounterSets * kCounterStride);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         if (p->d_tab) cudaFree(p->d_tab);
+        if (p->d_counters) cudaFree(p->d_counters);
         delete p;
         return cuda_fail(e, "dsk_perm_create upload");
     }
@@ -214,6 +223,7 @@ void dsk_perm_destroy(dsk_perm *p) {
         cudaGetDevice(&prev);
         cudaSetDevice(p->device);
         cudaFree(p->d_tab);
+        if (p->d_counters) cudaFree(p->d_counters);
         cudaSetDevice(prev);
     }
     delete p;
@@ -274,6 +284,8 @@ int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u6
     prm.init_is_u64 = init_is_u64;
     prm.out = d_out;
     prm.out_is_u64 = out_is_u64;
+    prm.work_counter = perm_counters(perm);
+    prm.docs_per_unit = 1;
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
     return DSK_OK;
 }
@@ -752,6 +764,8 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         prm.n_docs = nd;
         prm.n_tokens = nt;
         prm.out = hp.d_out[slot];
+        prm.work_counter = perm_counters(perm);
+        prm.docs_per_unit = 1;
         e = launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, st);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync((char *)h_out + (size_t)d0 * K * osz, hp.d_out[slot], (size_t)nd * K * osz,

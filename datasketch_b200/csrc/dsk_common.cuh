@@ -32,6 +32,8 @@ struct BulkParams {
     int init_is_u64;
     void *out;                  // [n_docs, k] u32 or u64
     int out_is_u64;
+    unsigned *work_counter;     // [K slices] device counters, zeroed by the launcher: dynamic unit distribution
+    int docs_per_unit;          // set by the launcher
 };
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
