@@ -329,8 +329,14 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg_bytes = (4 * t + 4 * k) * n  # per launch, per GPU
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this kernel/workload
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         h = nv.perm_handle(perms, local)
         kern = args.kernel if args.kernel != "auto" else ("two_phase" if h.n_unsafe == 0 else "exact")
+        if os.path.exists(tpath):
+            ent = json.load(open(tpath)).get("minhash_bulk_kernel<%s>|%dx%dxK%d" % (kern, n, t, k))
+            if ent:
+                traffic = ent["traffic_bytes_per_launch"] / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -340,7 +346,8 @@ def run_ours(args):
                        "kernel": "minhash_bulk_kernel<%s>" % kern, "l2": "inputs (%.2f GB/GPU) larger than L2"
                                    % (h_tok.nbytes / 1e9), "parallelism": "documents sharded x%d, no collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write; algorithmic %.3f GB)"
+                                                             % (alg_bytes / 1e9), "peak_source": peak_src,
                          "note": "binding roof is the integer pipe (T*K evaluations/doc), see DESIGN.md"},
             "e2e": e2e, "gpu_launches": args.steps + e2e_launches, "clocks": clocks,
         }
