@@ -34,64 +34,64 @@ struct LeanParams {
     int *status;           // unpack: set to 1 if any record header mismatches
 };
 
+constexpr int kLeanStages = 4;  // tiles in flight per CTA (loads) -- Little's law: ~100 KB in flight per SM
+
 template <bool PACK>
 __global__ void __launch_bounds__(kCodecThreads) lean_tile_kernel(const LeanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full[2];
+    __shared__ __align__(8) uint64_t full[kLeanStages];
     const int K = p.k, RW = p.k + 3, R = p.rows_per_tile;
-    const size_t in_words = (size_t)R * (PACK ? K : RW), out_words = (size_t)R * (PACK ? RW : K);
-    // layout: in[2] | out[2], each region 16-byte aligned (R % 4 == 0, K % 4 == 0 on this path)
-    uint32_t *sin[2] = {reinterpret_cast<uint32_t *>(smem), reinterpret_cast<uint32_t *>(smem) + in_words};
-    uint32_t *sout[2] = {sin[1] + in_words, sin[1] + in_words + out_words};
+    const int in_rw = PACK ? K : RW, out_rw = PACK ? RW : K;
+    const size_t in_words = (size_t)R * in_rw, out_words = (size_t)R * out_rw;
+    // layout: in[S] | out[S]; every region starts 16-byte aligned (R % 4 == 0, K % 4 == 0 on this path)
+    uint32_t *sin0 = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *sout0 = sin0 + kLeanStages * in_words;
     const uint32_t *gin = PACK ? p.sig : p.rec;
     uint32_t *gout = PACK ? p.rec : const_cast<uint32_t *>(p.sig);
-    const int in_rw = PACK ? K : RW, out_rw = PACK ? RW : K;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kCodecThreads / 32;
     const int64_t ntiles = (p.n + R - 1) / R;
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < kLeanStages; ++i) mbar_init(&full[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto load_tile = [&](int64_t t, int buf) {  // thread 0
+    auto load_tile = [&](int64_t t, int stage) {  // thread 0
         const int64_t r0 = t * R;
         const int nr = (int)min((int64_t)R, p.n - r0);
-        const uint32_t bytes = (uint32_t)((size_t)nr * in_rw * 4);
-        const uint32_t bulk = bytes & ~15u;
+        const uint32_t bulk = (uint32_t)((size_t)nr * in_rw * 4) & ~15u;
         if (bulk) {
-            mbar_arrive_expect_tx(&full[buf], bulk);
-            bulk_g2s(sin[buf], gin + (size_t)r0 * in_rw, bulk, &full[buf]);
+            mbar_arrive_expect_tx(&full[stage], bulk);
+            bulk_g2s(sin0 + stage * in_words, gin + (size_t)r0 * in_rw, bulk, &full[stage]);
         } else {
-            mbar_arrive(&full[buf]);
+            mbar_arrive(&full[stage]);
         }
     };
 
-    int64_t t = blockIdx.x;
-    if (tid == 0 && t < ntiles) load_tile(t, 0);
-    uint32_t phase[2] = {0, 0};
-    int buf = 0;
-    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+    if (tid == 0)
+        for (int i = 0; i < kLeanStages; ++i) {
+            const int64_t t = blockIdx.x + (int64_t)i * gridDim.x;
+            if (t < ntiles) load_tile(t, i);
+        }
+    int64_t it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int stage = (int)(it % kLeanStages);
+        const uint32_t phase = (uint32_t)((it / kLeanStages) & 1);
+        uint32_t *sin = sin0 + stage * in_words, *sout = sout0 + stage * out_words;
         const int64_t r0 = t * R;
         const int nr = (int)min((int64_t)R, p.n - r0);
-        const int64_t tn = t + gridDim.x;
-        if (tid == 0) {
-            if (tn < ntiles) load_tile(tn, buf ^ 1);  // prefetch (its previous readers passed the barrier below)
-            bulk_wait_read<1>();                       // the store that last used sout[buf] has read it
-        }
-        mbar_wait(&full[buf], phase[buf]);
-        phase[buf] ^= 1;
+        if (tid == 0) bulk_wait_read<kLeanStages - 1>();  // the store that last used sout[stage] has read it
+        mbar_wait(&full[stage], phase);
         {   // bytes beyond the last 16-byte granule of a ragged final tile come by plain loads
             const uint32_t words = (uint32_t)((size_t)nr * in_rw), bulk_words = words & ~3u;
-            if (tid < (int)(words - bulk_words)) sin[buf][bulk_words + tid] = gin[(size_t)r0 * in_rw + bulk_words + tid];
+            if (tid < (int)(words - bulk_words)) sin[bulk_words + tid] = gin[(size_t)r0 * in_rw + bulk_words + tid];
         }
         __syncthreads();
         // re-layout: warp <-> record, lane <-> word (conflict-free on both sides)
         for (int r = warp; r < nr; r += nwarps) {
-            const uint32_t *src = sin[buf] + (size_t)r * in_rw;
-            uint32_t *dst = sout[buf] + (size_t)r * out_rw;
+            const uint32_t *src = sin + (size_t)r * in_rw;
+            uint32_t *dst = sout + (size_t)r * out_rw;
             if (PACK) {
                 for (int c = lane; c < RW; c += 32) {
                     uint32_t v;
@@ -112,13 +112,15 @@ __global__ void __launch_bounds__(kCodecThreads) lean_tile_kernel(const LeanPara
             }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
-        __syncthreads();
+        __syncthreads();      // also: every reader of sin[stage] is done -> it can be refilled
         const uint32_t obytes = (uint32_t)((size_t)nr * out_rw * 4), obulk = obytes & ~15u;
         if (tid == 0) {
-            if (obulk) bulk_s2g(gout + (size_t)r0 * out_rw, sout[buf], obulk);
+            if (obulk) bulk_s2g(gout + (size_t)r0 * out_rw, sout, obulk);
             bulk_commit();
+            const int64_t tn = t + (int64_t)kLeanStages * gridDim.x;
+            if (tn < ntiles) load_tile(tn, stage);
         }
-        if (tid < (int)((obytes - obulk) / 4)) gout[(size_t)r0 * out_rw + obulk / 4 + tid] = sout[buf][obulk / 4 + tid];
+        if (tid < (int)((obytes - obulk) / 4)) gout[(size_t)r0 * out_rw + obulk / 4 + tid] = sout[obulk / 4 + tid];
     }
     if (tid == 0) bulk_wait_read<0>();
 }
@@ -171,7 +173,19 @@ __global__ void __launch_bounds__(256) band_keys_be_kernel(const uint32_t *__res
     for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
         const uint32_t *row = sig + i * k;
         uint2 *orow = out + i * br;
-        for (int c = lane; c < br; c += 32) orow[c] = make_uint2(0u, bswap32(row[c]));  // 00 00 00 00 b3 b2 b1 b0
+        for (int c0 = 0; c0 < br; c0 += 256) {  // 8 independent loads per lane before the first store
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32 + lane;
+                v[u] = c < br ? __ldg(row + c) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32 + lane;
+                if (c < br) orow[c] = make_uint2(0u, bswap32(v[u]));  // 00 00 00 00 b3 b2 b1 b0
+            }
+        }
     }
 }
 
@@ -206,10 +220,10 @@ static void lean_header(int64_t seed, int k, int big_endian, uint32_t &w0, uint3
 }
 
 static int lean_rows_per_tile(int k) {
-    // 2 x (in + out) tiles must fit ~96 KB so two CTAs share an SM
-    const size_t per_row = (size_t)(2 * k + 3) * 4 * 2;
-    int r = (int)((96 * 1024) / per_row) & ~3;
-    if (r > 64) r = 64;
+    // kLeanStages x (in + out) tiles in ~68 KB so three CTAs share an SM
+    const size_t per_row = (size_t)(2 * k + 3) * 4 * kLeanStages;
+    int r = (int)((68 * 1024) / per_row) & ~3;
+    if (r > 32) r = 32;
     return r;
 }
 
@@ -224,11 +238,11 @@ cudaError_t launch_lean_pack(const void *sig, int sig_is_u64, int64_t n, int k, 
         LeanParams p{};
         p.sig = static_cast<const uint32_t *>(sig); p.rec = reinterpret_cast<uint32_t *>(rec);
         p.n = n; p.k = k; p.rows_per_tile = R; p.w0 = w0; p.w1 = w1; p.w2 = w2; p.big_endian = big_endian;
-        const size_t smem = (size_t)R * (2 * k + 3) * 4 * 2;
+        const size_t smem = (size_t)R * (2 * k + 3) * 4 * kLeanStages;
         cudaError_t e = cudaFuncSetAttribute(lean_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (n + R - 1) / R;
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 2);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 3);
         lean_tile_kernel<true><<<grid, kCodecThreads, smem, s>>>(p);
     } else {
         const int64_t total = n * (k + 3);
@@ -251,11 +265,11 @@ cudaError_t launch_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t see
         p.sig = static_cast<const uint32_t *>(sig); p.rec = reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(rec));
         p.n = n; p.k = k; p.rows_per_tile = R; p.w0 = w0; p.w1 = w1; p.w2 = w2; p.big_endian = big_endian;
         p.status = d_status;
-        const size_t smem = (size_t)R * (2 * k + 3) * 4 * 2;
+        const size_t smem = (size_t)R * (2 * k + 3) * 4 * kLeanStages;
         cudaError_t e = cudaFuncSetAttribute(lean_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (n + R - 1) / R;
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 2);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 3);
         lean_tile_kernel<false><<<grid, kCodecThreads, smem, s>>>(p);
     } else {
         const int64_t total = n * (k + 3);

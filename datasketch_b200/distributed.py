@@ -89,3 +89,105 @@ def sharded_bulk_signatures(tokens: np.ndarray, offsets: np.ndarray, permutation
     for r, (a, b) in enumerate(bounds):
         out[a:b] = full[r * rows: r * rows + (b - a)]
     return out, (d0, d1)
+
+
+class ShardedLSH:
+    """MinHashLSH over documents sharded across ranks (config C3: insert + query on 8 GPUs).
+
+    Every rank owns a device-resident ``GpuLSH`` over *its* documents (all b bands).  Buckets never
+    span ranks' documents, so insert needs no communication.  ``query`` all-gathers the query
+    signatures (the one exchange of the path), every rank answers all queries against its shard, and
+    the answers return to the asking rank with two all-to-alls (per-query counts, then document
+    numbers).  Document numbers are global: rank r's i-th inserted document is ``base[r] + i``
+    where ``base`` is the exclusive prefix of the per-rank document counts.
+
+    ``index_factory`` exists for the CPU/gloo tests; the default is ``lsh.GpuLSH`` (no CPU fallback).
+    """
+
+    def __init__(self, threshold: float = 0.9, num_perm: int = 128, params=None, capacity: int = 1 << 20,
+                 group=None, index_factory: Optional[Callable] = None, device: Optional[int] = None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if index_factory is None:
+            from .lsh import GpuLSH
+            if device is None:
+                device = torch.cuda.current_device()
+            self.index = GpuLSH(threshold=threshold, num_perm=num_perm, params=params, capacity=capacity, device=device)
+        else:
+            self.index = index_factory(threshold=threshold, num_perm=num_perm, params=params, capacity=capacity)
+        self.h = num_perm
+        self.n_local = 0
+        self.base = 0
+        self.counts = [0] * self.world
+
+    def insert(self, sig_local) -> None:
+        """Insert this rank's signature block; renumbers the global document ids (collective)."""
+        import torch
+        import torch.distributed as dist
+        self.index.insert(sig_local)
+        self.n_local += int(sig_local.shape[0])
+        if self.world > 1:
+            t = torch.tensor([self.n_local], dtype=torch.int64, device=sig_local.device)
+            allc = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(allc, t, group=self.group)
+            self.counts = [int(x.item()) for x in allc]
+        else:
+            self.counts = [self.n_local]
+        self.base = sum(self.counts[: self.rank])
+
+    def query(self, sig_q_local):
+        """Candidates (global document numbers) of this rank's queries: ``(ptr int64[Q+1], idx int64[total])``
+        as tensors on the queries' device.  Collective: every rank must call it."""
+        import torch
+        import torch.distributed as dist
+        dev = sig_q_local.device
+        nq_me = int(sig_q_local.shape[0])
+        if self.world == 1:
+            ptr, idx = self.index.query(sig_q_local, to_host=False)
+            return ptr, idx.to(torch.int64)
+        # 1. all-gather the queries (padded to the largest per-rank count)
+        t = torch.tensor([nq_me], dtype=torch.int64, device=dev)
+        allq = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(allq, t, group=self.group)
+        nq = [int(x.item()) for x in allq]
+        rows = max(max(nq), 1)
+        padded = torch.zeros((rows, self.h), dtype=sig_q_local.dtype, device=dev)
+        padded[:nq_me] = sig_q_local
+        gathered = torch.empty((self.world * rows, self.h), dtype=sig_q_local.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, padded, group=self.group)
+        sel = torch.cat([torch.arange(r * rows, r * rows + nq[r], device=dev) for r in range(self.world)])
+        q_all = gathered[sel].contiguous()
+        # 2. answer every query against this rank's shard
+        ptr_all, idx_all = self.index.query(q_all, to_host=False)
+        idx_all = idx_all.to(torch.int64) + self.base
+        cnt_all = (ptr_all[1:] - ptr_all[:-1]).contiguous()
+        # 3. return answers to the asking ranks: counts, then payload
+        qoff = np.concatenate([[0], np.cumsum(nq)]).astype(np.int64)
+        cnt_back = torch.empty((self.world * nq_me,), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(cnt_back, cnt_all, [nq_me] * self.world, nq, group=self.group)
+        ptr_host = ptr_all.cpu().numpy()
+        send_sizes = [int(ptr_host[qoff[r + 1]] - ptr_host[qoff[r]]) for r in range(self.world)]
+        cnt_back2 = cnt_back.view(self.world, nq_me)
+        recv_sizes = [int(x) for x in cnt_back2.sum(dim=1).cpu().tolist()]
+        payload = torch.empty((sum(recv_sizes),), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(payload, idx_all, recv_sizes, send_sizes, group=self.group)
+        # 4. merge: a query's candidates = concatenation over source ranks (disjoint document sets)
+        tot = cnt_back2.sum(dim=0)
+        ptr = torch.zeros((nq_me + 1,), dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(tot, 0)
+        out = torch.empty((int(ptr[-1].item()),), dtype=torch.int64, device=dev)
+        before = torch.cumsum(cnt_back2, 0) - cnt_back2            # candidates of earlier source ranks, per query
+        pos0 = 0
+        for s in range(self.world):
+            c = cnt_back2[s]
+            n_s = recv_sizes[s]
+            if n_s:
+                src_excl = torch.cumsum(c, 0) - c
+                dest0 = ptr[:-1] + before[s]
+                shift = torch.repeat_interleave(dest0 - src_excl, c)
+                out[shift + torch.arange(n_s, device=dev)] = payload[pos0:pos0 + n_s]
+            pos0 += n_s
+        return ptr, out

@@ -73,3 +73,60 @@ def test_shard_bounds_properties():
             if n and off[-1] > 0:
                 per = [off[y] - off[x] for x, y in b]
                 assert max(per) <= off[-1] / world + np.diff(off).max()
+
+
+class _OracleIndex:
+    """Stand-in for GpuLSH in the CPU test: the dict oracle behind the same insert/query interface."""
+
+    def __init__(self, threshold, num_perm, params, capacity):
+        self.b, self.r = params
+        self.ix = o.DictLSH(num_perm, self.b, self.r)
+        self.n = 0
+
+    def insert(self, sig):
+        for row in sig.numpy().view(np.uint32).astype(np.uint64):
+            self.ix.insert(self.n, row)
+            self.n += 1
+
+    def query(self, sig, to_host=False):
+        ptr, idx = [0], []
+        for row in sig.numpy().view(np.uint32).astype(np.uint64):
+            idx.extend(sorted(self.ix.query(row)))
+            ptr.append(len(idx))
+        return torch.tensor(ptr, dtype=torch.int64), torch.tensor(idx, dtype=torch.int32)
+
+
+def _lsh_worker(rank, world, port, sig, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datasketch_b200.distributed import ShardedLSH
+    n = len(sig)
+    cut = [0, 130, n]                                   # uneven shards
+    mine = torch.from_numpy(sig[cut[rank]:cut[rank + 1]].view(np.int32).copy())
+    ix = ShardedLSH(num_perm=sig.shape[1], params=(8, 4), capacity=1000, index_factory=_OracleIndex)
+    ix.insert(mine)
+    assert ix.base == cut[rank] and ix.counts == [130, n - 130]
+    qsel = np.arange(rank, n, 3)                        # each rank asks about different documents
+    ptr, idx = ix.query(torch.from_numpy(sig[qsel].view(np.int32).copy()))
+    ret[rank] = (qsel, ptr.numpy().copy(), idx.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_lsh_gloo_world2():
+    rs = np.random.RandomState(9)
+    n, k = 300, 32
+    sig = rs.randint(0, 3, size=(n, k)).astype(np.uint32)
+    sig[rs.randint(0, n, 40)] = sig[rs.randint(0, n, 40)]
+    ref = o.DictLSH(k, 8, 4)
+    for i, row in enumerate(sig):
+        ref.insert(i, row.astype(np.uint64))
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_lsh_worker, args=(2, _free_port(), sig, ret), nprocs=2, join=True)
+    for rank in (0, 1):
+        qsel, ptr, idx = ret[rank]
+        assert ptr[0] == 0 and ptr[-1] == len(idx)
+        for j, qi in enumerate(qsel):
+            assert sorted(idx[ptr[j]:ptr[j + 1]].tolist()) == sorted(ref.query(sig[qi].astype(np.uint64)))
