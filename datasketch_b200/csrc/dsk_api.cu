@@ -598,6 +598,20 @@ int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int6
     return DSK_OK;
 }
 
+int dsk_sha1_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64_t n_tokens, void *d_out,
+                    int out_is_u64, void *stream) {
+    if (n_tokens < 0 || (n_tokens > 0 && (!d_byte_offsets || !d_out))) {
+        set_error("dsk_sha1_tokens: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_sha1_tokens(d_bytes, d_byte_offsets, n_tokens, d_out, out_is_u64, dev->sm_count,
+                                (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

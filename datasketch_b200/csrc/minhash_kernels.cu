@@ -494,9 +494,7 @@ static cudaError_t launch_bulk_p(const BulkParams &prm, int sm_count, cudaStream
         return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);
     }
     if (MODE == MODE_TWO_PHASE) {
-        static int k256 = [] { const char *e = getenv("DSK_K256_MODE"); return e ? atoi(e) : 0; }();
-        if (k256 == 1) return launch_bulk<8, MODE, TokT, 4>(prm, sm_count, s);
-        if (k256 == 2) return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);  // K slices of 128 via blockIdx.y
+        return launch_bulk<8, MODE, TokT, 4>(prm, sm_count, s);  // 119 registers, 4 CTAs/SM (measured best)
     }
     return launch_bulk<8, MODE, TokT, 3>(prm, sm_count, s);
 }

@@ -119,3 +119,49 @@ def bulk_signatures_device(d_tokens, d_offsets, n_tokens: int, permutations: np.
                                              int(d_init.element_size() == 8) if d_init is not None else 0,
                                              d_out.data_ptr(), out64, KERNELS[kernel], stream))
     return d_out
+
+
+def sha1_hash_tokens_device(flat_tokens, device: int = 0, out_u64: bool = False):
+    """Device-side ``sha1_hash32`` / ``sha1_hash64`` (datasketch/hashfunc.py:5-28) of a flat list of
+    byte strings -> CUDA tensor of hashes (int32 / int64 storage of the unsigned values)."""
+    import torch
+    nv.require_device(device)
+    n = len(flat_tokens)
+    lens = np.fromiter(map(len, flat_tokens), dtype=np.int64, count=n)
+    blob = b"".join(flat_tokens)  # TypeError for non-bytes tokens, like hashlib would raise
+    boff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=boff[1:])
+    dev = torch.device("cuda", device)
+    d_bytes = (torch.frombuffer(bytearray(blob), dtype=torch.uint8) if blob else torch.zeros(1, dtype=torch.uint8)).to(dev)
+    d_boff = torch.from_numpy(boff).to(dev)
+    out = torch.empty((max(n, 4),), dtype=torch.int64 if out_u64 else torch.int32, device=dev)
+    with torch.cuda.device(device):
+        nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n, out.data_ptr(), int(out_u64),
+                                            torch.cuda.current_stream(dev).cuda_stream))
+    return out[:n] if n >= 4 else out
+
+
+def bulk_signatures_sha1(docs: Sequence[Sequence[bytes]], permutations: np.ndarray, init: Optional[np.ndarray] = None,
+                         device: int = 0) -> np.ndarray:
+    """``MinHash.bulk`` for byte tokens under the DEFAULT hash function, entirely on device:
+    SHA1-32 of every token (``dsk_sha1_tokens``) feeds the signature kernel without the hashes ever
+    visiting the host.  Returns the [N, K] uint64 matrix (the reference's dtype)."""
+    import torch
+    n = len(docs)
+    doc_lens = np.fromiter(map(len, docs), dtype=np.int64, count=n)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(doc_lens, out=off[1:])
+    flat = [t for d in docs for t in d]
+    n_tok = len(flat)
+    d_hash = sha1_hash_tokens_device(flat, device)
+    dev = d_hash.device
+    d_off = torch.from_numpy(off).to(dev)
+    d_out = torch.empty((n, permutations.shape[1]), dtype=torch.int64, device=dev)
+    d_init, stride = None, 0
+    if init is not None:
+        init = np.ascontiguousarray(init, dtype=np.uint64)
+        d_init = torch.from_numpy(init.view(np.int64)).to(dev)
+        stride = 0 if init.ndim == 1 else init.shape[1]
+    if n:
+        bulk_signatures_device(d_hash, d_off, n_tok, permutations, d_out=d_out, d_init=d_init, init_stride=stride)
+    return d_out.cpu().numpy().view(np.uint64)

@@ -213,20 +213,34 @@ class MinHash:
         hf = proto.hashfunc
         batch: List[List[int]] = []
 
-        def run(docs):
-            tok, off = engine.pack_docs(docs)
+        # With the reference's default hash function on byte tokens, hashing moves to the device too
+        # (dsk_sha1_tokens): same values as hashfunc.sha1_hash32, no per-token Python hashlib call.
+        device_sha1 = hf is sha1_hash32
+
+        def run(docs, hashed):
             init = proto.hashvalues if not proto.is_empty() else None
-            sig = engine.bulk_signatures(tok, off, perms, init=init, out_u64=True)
+            if hashed:
+                tok, off = engine.pack_docs(docs)
+                sig = engine.bulk_signatures(tok, off, perms, init=init, out_u64=True)
+            else:
+                sig = engine.bulk_signatures_sha1(docs, perms, init=init)
             for row in sig:
                 yield cls._from_row(proto, row.copy())
 
+        raw_ok = device_sha1
         for doc in b:
-            batch.append([hf(t) for t in doc])
+            doc = doc if isinstance(doc, (list, tuple)) else list(doc)
+            if raw_ok and not all(isinstance(t, (bytes, bytearray)) for t in doc):
+                # a non-bytes token: fall back to calling the hash function per token (it will raise as usual)
+                batch = [[hf(t) for t in d] for d in batch]
+                raw_ok = False
+            batch.append(doc if raw_ok else [hf(t) for t in doc])
             if len(batch) >= batch_docs:
-                yield from run(batch)
+                yield from run(batch, hashed=not raw_ok)
                 batch = []
+                raw_ok = device_sha1
         if batch:
-            yield from run(batch)
+            yield from run(batch, hashed=not raw_ok)
 
     # -- pickling: only host state travels (cf. minhash.py:529-537) ---------------------------------
     def __getstate__(self):

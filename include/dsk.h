@@ -181,6 +181,14 @@ DSK_API int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_per
 DSK_API int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
                              int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *stream);
 
+/* ---- default token hash on device ("next" row) --------------------------------
+ * d_out[t] = sha1_hash32 (out_is_u64 = 0) or sha1_hash64 (= 1) of the byte string
+ * d_bytes[d_byte_offsets[t] : d_byte_offsets[t+1]] -- datasketch/hashfunc.py:5-28, i.e. the
+ * first 4 / 8 bytes of SHA-1 read little-endian.  Lets MinHash.bulk with the default hashfunc
+ * skip the per-token Python hashlib loop (minhash.py:263). */
+DSK_API int dsk_sha1_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64_t n_tokens, void *d_out,
+                            int out_is_u64, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
