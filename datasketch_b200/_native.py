@@ -38,6 +38,8 @@ SIGNATURES = {
     "dsk_perm_analyze": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "dsk_minhash_bulk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),
+    "dsk_minhash_bulk_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int,
+                                        c_int64, c_int, c_int, c_void_p]),
     "dsk_minhash_bulk_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_void_p, c_int, c_int]),
     "dsk_sig_merge_min": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -286,6 +286,56 @@ int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u6
     prm.out_is_u64 = out_is_u64;
     prm.work_counter = perm_counters(perm);
     prm.docs_per_unit = 1;
+    prm.n_peers = 0;
+    prm.peer_row_offset = 0;
+    DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int token_is_u64, const int64_t *d_offsets,
+                            int64_t n_docs, int64_t n_tokens, void *const *h_peer_out, int n_peers,
+                            int64_t row_offset, int out_is_u64, int flags, void *stream) {
+    if (!perm || !d_offsets || !h_peer_out || n_peers < 1 || n_peers > 8 || n_docs < 0 || n_tokens < 0 ||
+        row_offset < 0 || (n_tokens > 0 && !d_tokens)) {
+        set_error("dsk_minhash_bulk_gather: bad arguments (1 <= n_peers <= 8)");
+        return DSK_ERR_INVALID;
+    }
+    if (n_docs == 0) return DSK_OK;
+    if (((uintptr_t)d_tokens & 15) != 0) {
+        set_error("dsk_minhash_bulk_gather: d_tokens must be 16-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    int mode;
+    int rc = pick_mode(perm, token_is_u64, flags, &mode);
+    if (rc) return rc;
+    DevInfo *dev;
+    rc = get_dev(perm->device, &dev);
+    if (rc) return rc;
+    BulkParams prm;
+    prm.tokens = d_tokens;
+    prm.offsets = d_offsets;
+    prm.n_docs = n_docs;
+    prm.n_tokens = n_tokens;
+    prm.a_lo = perm->d_tab;
+    prm.a_hi = perm->d_tab + perm->kpad;
+    prm.b_lo = perm->d_tab + 2 * perm->kpad;
+    prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.k = perm->num_perm;
+    prm.init = nullptr;
+    prm.init_stride = 0;
+    prm.init_is_u64 = 0;
+    prm.out = nullptr;
+    prm.out_is_u64 = out_is_u64;
+    prm.work_counter = perm_counters(perm);
+    prm.docs_per_unit = 1;
+    prm.n_peers = n_peers;
+    prm.peer_row_offset = row_offset;
+    for (int i = 0; i < 8; ++i) prm.peer_out[i] = i < n_peers ? h_peer_out[i] : nullptr;
+    for (int i = 0; i < n_peers; ++i)
+        if (!h_peer_out[i] || ((uintptr_t)h_peer_out[i] & 15) != 0) {
+            set_error("dsk_minhash_bulk_gather: peer pointer %d is null or not 16-byte aligned", i);
+            return DSK_ERR_ALIGN;
+        }
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
     return DSK_OK;
 }
@@ -780,6 +830,8 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         prm.out = hp.d_out[slot];
         prm.work_counter = perm_counters(perm);
         prm.docs_per_unit = 1;
+        prm.n_peers = 0;
+        prm.peer_row_offset = 0;
         e = launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, st);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync((char *)h_out + (size_t)d0 * K * osz, hp.d_out[slot], (size_t)nd * K * osz,

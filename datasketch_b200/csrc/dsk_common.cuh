@@ -34,6 +34,11 @@ struct BulkParams {
     int out_is_u64;
     unsigned *work_counter;     // [K slices] device counters, zeroed by the launcher: dynamic unit distribution
     int docs_per_unit;          // set by the launcher
+    // fused all-gather epilogue: when n_peers > 0 every signature row is stored into each peer_out[p]
+    // (the full [N_total, k] matrix of rank p, mapped peer memory) at row peer_row_offset + d
+    int n_peers;
+    int64_t peer_row_offset;
+    void *peer_out[8];
 };
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);

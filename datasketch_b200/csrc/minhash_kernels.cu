@@ -418,24 +418,31 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                 }
             }
         }
-        if (prm.out_is_u64) {
-            uint64_t *row = static_cast<uint64_t *>(prm.out) + d * (int64_t)K + kl;
-#pragma unroll
-            for (int j = 0; j < P; ++j)
-                if (kl + j < K) row[j] = res[j];
-        } else {
-            uint32_t *row = static_cast<uint32_t *>(prm.out) + d * (int64_t)K + kl;
-            if (P == 4 && (K & 3) == 0) {
-                if (kl < K) *reinterpret_cast<uint4 *>(row) = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
-            } else if (P == 8 && (K & 7) == 0) {
-                if (kl < K) {
-                    reinterpret_cast<uint4 *>(row)[0] = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
-                    reinterpret_cast<uint4 *>(row)[1] = make_uint4(res[4 % P], res[5 % P], res[6 % P], res[7 % P]);
-                }
-            } else {
+        // One store per destination: the caller's matrix, or -- fused all-gather -- the same row of the full
+        // [N_total, K] matrix on EVERY rank (peer pointers mapped over NVLink; plain st.global to a peer address).
+        const int n_dst = prm.n_peers > 0 ? prm.n_peers : 1;
+        for (int pd = 0; pd < n_dst; ++pd) {
+            void *obase = prm.n_peers > 0 ? prm.peer_out[pd] : prm.out;
+            const int64_t orow = d + (prm.n_peers > 0 ? prm.peer_row_offset : 0);
+            if (prm.out_is_u64) {
+                uint64_t *row = static_cast<uint64_t *>(obase) + orow * (int64_t)K + kl;
 #pragma unroll
                 for (int j = 0; j < P; ++j)
                     if (kl + j < K) row[j] = res[j];
+            } else {
+                uint32_t *row = static_cast<uint32_t *>(obase) + orow * (int64_t)K + kl;
+                if (P == 4 && (K & 3) == 0) {
+                    if (kl < K) *reinterpret_cast<uint4 *>(row) = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
+                } else if (P == 8 && (K & 7) == 0) {
+                    if (kl < K) {
+                        reinterpret_cast<uint4 *>(row)[0] = make_uint4(res[0], res[1 % P], res[2 % P], res[3 % P]);
+                        reinterpret_cast<uint4 *>(row)[1] = make_uint4(res[4 % P], res[5 % P], res[6 % P], res[7 % P]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < P; ++j)
+                        if (kl + j < K) row[j] = res[j];
+                }
             }
         }
         start = end;

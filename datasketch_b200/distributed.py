@@ -191,3 +191,61 @@ class ShardedLSH:
                 out[shift + torch.arange(n_s, device=dev)] = payload[pos0:pos0 + n_s]
             pos0 += n_s
         return ptr, out
+
+
+class FusedGather:
+    """Signature build fused with the all-gather (NVLink peer stores instead of a separate NCCL pass).
+
+    Holds a symmetric-memory [n_total, K] int32 matrix (``torch.distributed._symmetric_memory``:
+    every rank's buffer is mapped into every other rank's address space over NVLink/NVSwitch).
+    ``build`` runs ``dsk_minhash_bulk_gather``: the kernel stores each finished signature row into
+    the same row of all ranks' matrices, so the transfer overlaps the integer math document by
+    document; a stream sync + barrier then makes the full matrix valid on every rank.
+    """
+
+    def __init__(self, n_total: int, num_perm: int, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("FusedGather supports up to 8 ranks (one NVSwitch domain)")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else device
+        self.n_total, self.k = int(n_total), int(num_perm)
+        self.buf = symm_mem.empty((self.n_total, self.k), dtype=torch.int32, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def build(self, d_tokens, d_offsets, n_tokens: int, permutations: np.ndarray, row_offset: int,
+              kernel: str = "auto", sync: bool = True):
+        """This rank's documents -> rows [row_offset, row_offset + n_docs) of every rank's matrix."""
+        import ctypes
+        import torch
+        from . import _native as nv
+        from .engine import KERNELS
+        n = d_offsets.numel() - 1
+        if row_offset < 0 or row_offset + n > self.n_total:
+            raise ValueError("row range exceeds the gathered matrix")
+        h = nv.perm_handle(permutations, self.device.index)
+        if h.num_perm != self.k:
+            raise ValueError("num_perm mismatch")
+        arr = (ctypes.c_void_p * self.world)(*self.ptrs)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device)
+            nv.check(nv.load().dsk_minhash_bulk_gather(h.handle, d_tokens.data_ptr() if n_tokens else None,
+                                                        int(d_tokens.element_size() == 8), d_offsets.data_ptr(), n,
+                                                        n_tokens, ctypes.cast(arr, ctypes.c_void_p), self.world,
+                                                        row_offset, 0, KERNELS[kernel], st.cuda_stream))
+            if sync:
+                self.finish()
+        return self.buf
+
+    def finish(self) -> None:
+        """All ranks' peer stores have landed: stream sync, then a cross-rank barrier."""
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+        self.hdl.barrier()

@@ -93,6 +93,17 @@ DSK_API int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int tok
                      const void *d_init, int64_t init_stride, int init_is_u64,
                      void *d_out, int out_is_u64, int flags, void *stream);
 
+/* Fused signature build + all-gather (multi-GPU): like dsk_minhash_bulk, but each signature row
+ * is stored straight into row (row_offset + i) of the FULL [N_total, num_perm] matrix of every
+ * rank: h_peer_out[0..n_peers) are device pointers to those matrices (this rank's own buffer
+ * and its peers' buffers mapped over NVLink, e.g. torch symmetric memory / cudaIpc).  The
+ * transfer overlaps the integer math document by document; the caller synchronises the ranks
+ * afterwards (stream sync + barrier).  Replaces "build, then ncclAllGather". */
+DSK_API int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int token_is_u64,
+                                    const int64_t *d_offsets, int64_t n_docs, int64_t n_tokens,
+                                    void *const *h_peer_out, int n_peers, int64_t row_offset,
+                                    int out_is_u64, int flags, void *stream);
+
 /* Host-buffer variant: same computation, tokens/offsets/out are HOST pointers
  * (pinned memory gives full PCIe overlap; pageable memory is staged).  Documents
  * are cut into slices and H2D copy, kernel and D2H copy are pipelined over
