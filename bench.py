@@ -147,6 +147,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (what `numactl` would do), so the
+    pinned host buffers of the e2e leg are first-touched on the local node.  Best effort; returns a note."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return "numa: unknown"
+        if len(bus.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return "numa: node %d (%d cpus)" % (node, len(cpus))
+    except Exception as exc:  # noqa: BLE001
+        return "numa: not bound (%s)" % type(exc).__name__
+
+
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (its numpy uint64
@@ -202,9 +225,11 @@ def run_ours(args):
                "sample": "%d docs x %d tokens once (%.1f s wall), numpy uint64 path of datasketch over %d processes"
                          % (sample, t, dt, cores)}
 
+    numa_note = bind_to_gpu_numa_node(local)   # after the CPU baseline (which uses every core)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     perms = _make_permutations(k, 1)
@@ -373,7 +398,8 @@ def run_ours(args):
             "config": {"workload": "configs[1]: %d docs x %d tokens, num_perm=%d bulk signature build per GPU"
                                    % (n, t, k),
                        "kernel": "minhash_bulk_kernel<%s>" % kern, "l2": "inputs (%.2f GB/GPU) larger than L2"
-                                   % (h_tok.nbytes / 1e9), "parallelism": "documents sharded x%d, no collective" % world},
+                                   % (h_tok.nbytes / 1e9), "parallelism": "documents sharded x%d, no collective" % world,
+                       "host": numa_note},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write; algorithmic %.3f GB)"
                                                              % (alg_bytes / 1e9), "peak_source": peak_src,

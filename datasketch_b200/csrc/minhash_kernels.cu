@@ -205,9 +205,7 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
         for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; widx[j] = 0; }
 
         // one 16-token block (the hot code: 64 IMAD + 32 VIMNMX3 + 20 tracking ops for P=4)
-        auto process = [&](const TokT *src, uint32_t lb) {
-            TokT t[kBlkTok];
-            TokLoad<TokT>::block(src, t);
+        auto compute = [&](const TokT (&t)[kBlkTok], uint32_t lb) {
             if constexpr (MODE == MODE_TWO_PHASE) {
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
@@ -242,6 +240,11 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                     for (int i = 0; i < kBlkTok; ++i) m[j] = min(m[j], eval_exact(a64, b64, (uint64_t)t[i]));
                 }
             }
+        };
+        auto process = [&](const TokT *src, uint32_t lb) {
+            TokT t[kBlkTok];
+            TokLoad<TokT>::block(src, t);
+            compute(t, lb);
         };
 
         const int64_t dblk0 = start / kBlkTok;
@@ -279,8 +282,25 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                     const TokT *q = p + i * kBlkTok;
                     const TokT *const qe = p + nfull * kBlkTok;
                     uint32_t lb = lb0 + (uint32_t)i;
+                    if (q < qe) {
+                        // software pipeline (two register buffers): the next block's four LDS.128 are in
+                        // flight while the current block's 64 IMADs issue, so the loop never waits on smem
+                        TokT ta[kBlkTok], tb[kBlkTok];
+                        TokLoad<TokT>::block(q, ta);
 #pragma unroll 1
-                    for (; q < qe; q += kBlkTok, ++lb) process(q, lb);
+                        while (true) {
+                            const TokT *q1 = q + kBlkTok;
+                            if (q1 < qe) TokLoad<TokT>::block(q1, tb);
+                            compute(ta, lb);
+                            if (q1 >= qe) break;
+                            const TokT *q2 = q1 + kBlkTok;
+                            if (q2 < qe) TokLoad<TokT>::block(q2, ta);
+                            compute(tb, lb + 1);
+                            if (q2 >= qe) break;
+                            q = q2;
+                            lb += 2;
+                        }
+                    }
                 }
                 if (tp && nb > 1) patched(nb - 1);
                 blk += nb;
