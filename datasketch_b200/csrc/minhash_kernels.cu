@@ -282,7 +282,10 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                     const TokT *q = p + i * kBlkTok;
                     const TokT *const qe = p + nfull * kBlkTok;
                     uint32_t lb = lb0 + (uint32_t)i;
-                    if (q < qe) {
+                    if constexpr (P > 4) {   // 8 permutations per lane: registers are better spent on the evaluations
+#pragma unroll 1
+                        for (; q < qe; q += kBlkTok, ++lb) process(q, lb);
+                    } else if (q < qe) {
                         // software pipeline (two register buffers): the next block's four LDS.128 are in
                         // flight while the current block's 64 IMADs issue, so the loop never waits on smem
                         TokT ta[kBlkTok], tb[kBlkTok];
