@@ -31,7 +31,7 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
 
 n, t, k = a.docs_per_gpu, a.tokens, a.num_perm
