@@ -673,12 +673,17 @@ struct HostPipe {
     void *d_out[kSlots] = {};
     void *d_init[kSlots] = {};
     int64_t *h_off[kSlots] = {};  // pinned staging for rebased offsets
-    size_t cap_tok = 0, cap_docs = 0, cap_out = 0, cap_init = 0;
+    // long documents are split into pieces: partial signatures + segment pointers
+    uint32_t *d_part[kSlots] = {};
+    int64_t *d_seg[kSlots] = {};
+    int64_t *h_seg[kSlots] = {};
+    size_t cap_tok = 0, cap_docs = 0, cap_out = 0, cap_init = 0, cap_part = 0, cap_seg = 0;
 };
 HostPipe g_pipe[64];
 std::mutex g_pipe_mu;
 
-int pipe_reserve(HostPipe &hp, int device, size_t tok_bytes, size_t docs, size_t out_bytes, size_t init_bytes) {
+int pipe_reserve(HostPipe &hp, int device, size_t tok_bytes, size_t docs, size_t out_bytes, size_t init_bytes,
+                 size_t part_bytes, size_t seg_docs) {
     if (hp.device < 0) {
         for (int i = 0; i < kSlots; ++i) DSK_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
         hp.device = device;
@@ -709,6 +714,25 @@ int pipe_reserve(HostPipe &hp, int device, size_t tok_bytes, size_t docs, size_t
             DSK_CUDA(cudaMalloc(&hp.d_out[i], out_bytes + 64));
         }
         hp.cap_out = out_bytes;
+    }
+    if (part_bytes > hp.cap_part) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (hp.d_part[i]) cudaFree(hp.d_part[i]);
+            hp.d_part[i] = nullptr;
+            DSK_CUDA(cudaMalloc(&hp.d_part[i], part_bytes + 64));
+        }
+        hp.cap_part = part_bytes;
+    }
+    if (seg_docs > hp.cap_seg) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (hp.d_seg[i]) cudaFree(hp.d_seg[i]);
+            if (hp.h_seg[i]) cudaFreeHost(hp.h_seg[i]);
+            hp.d_seg[i] = nullptr;
+            hp.h_seg[i] = nullptr;
+            DSK_CUDA(cudaMalloc(&hp.d_seg[i], (seg_docs + 1) * sizeof(int64_t)));
+            DSK_CUDA(cudaMallocHost(&hp.h_seg[i], (seg_docs + 1) * sizeof(int64_t)));
+        }
+        hp.cap_seg = seg_docs;
     }
     if (init_bytes > hp.cap_init) {
         for (int i = 0; i < kSlots; ++i) {
@@ -753,10 +777,15 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
     DSK_CUDA(cudaSetDevice(perm->device));
     HostPipe &hp = g_pipe[perm->device];
 
+    // Long documents are cut into pieces so that many warps work on them (one warp per document otherwise);
+    // the pieces' partial signatures are min-merged on the device (seg_min_kernel).
+    auto piece_len = [](int64_t slice_tokens) -> int64_t { return slice_tokens < (2ll << 20) ? 2048 : 8192; };
+    auto n_pieces = [](int64_t len, int64_t piece) -> int64_t { return len > 2 * piece ? (len + piece - 1) / piece : 1; };
+
     // first pass: slice boundaries (a single document larger than max_tok gets its own slice)
     std::vector<int64_t> cut;
     cut.push_back(0);
-    int64_t biggest_tok = 0, biggest_docs = 0;
+    int64_t biggest_tok = 0, biggest_docs = 0, biggest_ext = 0, biggest_split_docs = 0;
     {
         int64_t d0 = 0;
         while (d0 < n_docs) {
@@ -770,6 +799,15 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
             }
             biggest_tok = biggest_tok > h_offsets[d1] - t0 ? biggest_tok : h_offsets[d1] - t0;
             biggest_docs = biggest_docs > d1 - d0 ? biggest_docs : d1 - d0;
+            {
+                const int64_t piece = piece_len(h_offsets[d1] - t0);
+                int64_t ext = 0;
+                for (int64_t i = d0; i < d1; ++i) ext += n_pieces(h_offsets[i + 1] - h_offsets[i], piece);
+                if (ext != d1 - d0) {
+                    biggest_ext = biggest_ext > ext ? biggest_ext : ext;
+                    biggest_split_docs = biggest_split_docs > d1 - d0 ? biggest_split_docs : d1 - d0;
+                }
+            }
             cut.push_back(d1);
             d0 = d1;
         }
@@ -781,8 +819,10 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         set_error("dsk_minhash_bulk_host: init_stride must be 0 or >= num_perm");
         return DSK_ERR_INVALID;
     }
-    rc = pipe_reserve(hp, perm->device, (size_t)biggest_tok * tsz, (size_t)biggest_docs, (size_t)biggest_docs * K * osz,
-                      init_rows * (size_t)(init_stride ? init_stride : K) * isz);
+    rc = pipe_reserve(hp, perm->device, (size_t)biggest_tok * tsz,
+                      (size_t)(biggest_docs > biggest_ext ? biggest_docs : biggest_ext), (size_t)biggest_docs * K * osz,
+                      init_rows * (size_t)(init_stride ? init_stride : K) * isz, (size_t)biggest_ext * K * sizeof(uint32_t),
+                      (size_t)biggest_split_docs);
     if (rc) {
         cudaSetDevice(prev);
         return rc;
@@ -808,31 +848,64 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         // the pinned offsets staging buffer of this slot is reused: wait for its previous slice
         if (s >= (size_t)kSlots) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) break;
-        for (int64_t i = 0; i <= nd; ++i) hp.h_off[slot][i] = h_offsets[d0 + i] - t0;
+        // offsets of this slice, rebased; documents above the split threshold become several pieces
+        const int64_t piece = piece_len(nt);
+        int64_t n_ext = 0;
+        for (int64_t i = d0; i < d1; ++i) n_ext += n_pieces(h_offsets[i + 1] - h_offsets[i], piece);
+        const bool split = n_ext != nd;
+        if (!split) {
+            for (int64_t i = 0; i <= nd; ++i) hp.h_off[slot][i] = h_offsets[d0 + i] - t0;
+        } else {
+            int64_t w = 0;
+            for (int64_t i = d0; i < d1; ++i) {
+                const int64_t b = h_offsets[i] - t0, len = h_offsets[i + 1] - h_offsets[i];
+                const int64_t np = n_pieces(len, piece);
+                hp.h_seg[slot][i - d0] = w;
+                for (int64_t q = 0; q < np; ++q) hp.h_off[slot][w++] = b + (np == 1 ? 0 : q * piece);
+            }
+            hp.h_seg[slot][nd] = w;
+            hp.h_off[slot][w] = nt;
+        }
         if (nt > 0)
             e = cudaMemcpyAsync(hp.d_tok[slot], (const char *)h_tokens + (size_t)t0 * tsz, (size_t)nt * tsz,
                                 cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(hp.d_off[slot], hp.h_off[slot], (size_t)(nd + 1) * sizeof(int64_t),
+            e = cudaMemcpyAsync(hp.d_off[slot], hp.h_off[slot], (size_t)(n_ext + 1) * sizeof(int64_t),
                                 cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && split)
+            e = cudaMemcpyAsync(hp.d_seg[slot], hp.h_seg[slot], (size_t)(nd + 1) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, st);
+        const void *slice_init = nullptr;
         if (e == cudaSuccess && h_init) {
             const size_t rows = init_stride == 0 ? 1 : (size_t)nd;
             const size_t row_elems = (size_t)(init_stride ? init_stride : K);
             const char *src = (const char *)h_init + (init_stride == 0 ? 0 : (size_t)d0 * row_elems * isz);
             e = cudaMemcpyAsync(hp.d_init[slot], src, rows * row_elems * isz, cudaMemcpyHostToDevice, st);
-            prm.init = hp.d_init[slot];
+            slice_init = hp.d_init[slot];
         }
         if (e != cudaSuccess) break;
         prm.tokens = hp.d_tok[slot];
         prm.offsets = hp.d_off[slot];
-        prm.n_docs = nd;
+        prm.n_docs = n_ext;
         prm.n_tokens = nt;
-        prm.out = hp.d_out[slot];
         prm.work_counter = perm_counters(perm);
         prm.docs_per_unit = 1;
         prm.n_peers = 0;
         prm.peer_row_offset = 0;
-        e = launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, st);
+        if (!split) {
+            prm.init = slice_init;
+            prm.out = hp.d_out[slot];
+            prm.out_is_u64 = out_is_u64;
+            e = launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, st);
+        } else {
+            prm.init = nullptr;
+            prm.out = hp.d_part[slot];
+            prm.out_is_u64 = 0;
+            e = launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, st);
+            if (e == cudaSuccess)
+                e = launch_seg_min(hp.d_part[slot], hp.d_seg[slot], nd, K, slice_init, init_stride, init_is_u64,
+                                   hp.d_out[slot], out_is_u64, dev->sm_count, st);
+        }
         if (e == cudaSuccess)
             e = cudaMemcpyAsync((char *)h_out + (size_t)d0 * K * osz, hp.d_out[slot], (size_t)nd * K * osz,
                                 cudaMemcpyDeviceToHost, st);

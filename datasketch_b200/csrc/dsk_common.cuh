@@ -42,6 +42,9 @@ struct BulkParams {
 };
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
+cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
+                           int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,
+                           cudaStream_t s);
 cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n, uint32_t *out, int sm_count,
                                  cudaStream_t s);
 

@@ -480,6 +480,39 @@ __global__ void sig_merge_min_kernel(const uint32_t *__restrict__ x, const uint3
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = min(x[i], y[i]);
 }
 
+// ---- segmented min: partial signatures of one split document -> its signature --------------------
+// A document longer than the split threshold is cut into pieces by the host pipeline so that many
+// warps work on it; signatures of pieces combine by element-wise min (minhash.py:337-359).
+__global__ void __launch_bounds__(256) seg_min_kernel(const uint32_t *__restrict__ part, const int64_t *__restrict__ seg,
+                                                      int64_t n_docs, int k, const void *__restrict__ init,
+                                                      int64_t init_stride, int init_is_u64, void *__restrict__ out,
+                                                      int out_is_u64) {
+    const int64_t total = n_docs * k, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t d = e / k;
+        const int c = (int)(e - d * k);
+        uint32_t v = 0xFFFFFFFFu;
+        for (int64_t r = seg[d]; r < seg[d + 1]; ++r) v = min(v, part[r * k + c]);
+        if (init != nullptr) {
+            const int64_t ie = d * init_stride + c;
+            if (init_is_u64) v = (uint32_t)min((uint64_t)v, static_cast<const uint64_t *>(init)[ie]);
+            else v = min(v, static_cast<const uint32_t *>(init)[ie]);
+        }
+        if (out_is_u64) static_cast<uint64_t *>(out)[e] = v;
+        else static_cast<uint32_t *>(out)[e] = v;
+    }
+}
+
+cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
+                           int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,
+                           cudaStream_t s) {
+    if (n_docs <= 0) return cudaSuccess;
+    int64_t grid = (n_docs * k + 255) / 256;
+    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+    seg_min_kernel<<<(unsigned)grid, 256, 0, s>>>(part, seg, n_docs, k, init, init_stride, init_is_u64, out, out_is_u64);
+    return cudaGetLastError();
+}
+
 // ---- launchers --------------------------------------------------------------------------------
 template <int P, int MODE, typename TokT, int OCC>
 static cudaError_t launch_bulk(const BulkParams &prm_in, int sm_count, cudaStream_t s) {

@@ -237,3 +237,24 @@ def test_medium_batch_sampled_against_oracle(dsk, kernel):
     half = np.arange(2 * n + 1, dtype=np.int64) * (t // 2)
     parts = dsk.engine.bulk_signatures(tok, half, P, kernel=kernel)
     assert np.array_equal(np.minimum(parts[0::2], parts[1::2]), sig)
+
+
+@pytest.mark.parametrize("kernel", ["auto", "exact"])
+def test_long_documents_are_split_and_merged(dsk, kernel):
+    # host pipeline cuts documents above the threshold into pieces (many warps) and min-merges on device
+    rs = np.random.RandomState(21)
+    P = o.init_permutations(128, 1)
+    lens = [5000, 0, 17, 4096, 4097, 70_000, 3, 0, 2_500_000, 129]
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 2 ** 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    want = oc.minhash_bulk_u32tok(tok, off, P)
+    got = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel)
+    assert np.array_equal(got, want)
+    init = rs.randint(0, 2 ** 32, size=(len(lens), 128), dtype=np.uint64)
+    got64 = dsk.engine.bulk_signatures(tok, off, P, kernel=kernel, init=init, out_u64=True)
+    assert got64.dtype == np.uint64 and np.array_equal(got64, np.minimum(init, want.astype(np.uint64)))
+    # the reference's own GPU benchmark shape: one update_batch of 50 000 tokens (docs/minhash.rst:161-169)
+    m = dsk.MinHash(num_perm=128, seed=1, hashfunc=int)
+    m.update_batch(int(x) for x in tok[:50_000])
+    assert np.array_equal(m.hashvalues, oc.minhash_bulk_u32tok(tok[:50_000], np.array([0, 50_000]), P)[0].astype(np.uint64))
