@@ -258,3 +258,32 @@ def test_long_documents_are_split_and_merged(dsk, kernel):
     m = dsk.MinHash(num_perm=128, seed=1, hashfunc=int)
     m.update_batch(int(x) for x in tok[:50_000])
     assert np.array_equal(m.hashvalues, oc.minhash_bulk_u32tok(tok[:50_000], np.array([0, 50_000]), P)[0].astype(np.uint64))
+
+
+def test_full_size_c2_properties(dsk):
+    """BASELINE.json configs[1] at full size (1M docs x 256 tokens, K=128): size-independent properties
+    plus a sampled comparison with the C oracle."""
+    n, t, k = 1_000_000, 256, 128
+    rng = np.random.default_rng(1234)
+    tok = np.empty(n * t, dtype=np.uint32)
+    step = 1 << 24
+    for i in range(0, tok.size, step):
+        tok[i:i + step] = rng.integers(0, 1 << 32, size=min(step, tok.size - i), dtype=np.uint32)
+    off = np.arange(n + 1, dtype=np.int64) * t
+    P = o.init_permutations(k, 1)
+    sig = dsk.engine.bulk_signatures(tok, off, P)
+    assert sig.shape == (n, k) and sig.dtype == np.uint32
+    # (1) sampled rows equal the oracle
+    idx = np.arange(0, n, 9973)
+    sub = np.ascontiguousarray(tok.reshape(n, t)[idx]).reshape(-1)
+    assert np.array_equal(sig[idx], oc.minhash_bulk_u32tok(sub, np.arange(len(idx) + 1, dtype=np.int64) * t, P))
+    # (2) splitting every document in two and min-merging the halves changes nothing (merge rule, minhash.py:359)
+    half = np.arange(2 * n + 1, dtype=np.int64) * (t // 2)
+    parts = dsk.engine.bulk_signatures(tok, half, P)
+    assert np.array_equal(np.minimum(parts[0::2], parts[1::2]), sig)
+    del parts
+    # (3) the direct kernel (different arithmetic path) produces the identical matrix: checksum of checksums
+    sig_d = dsk.engine.bulk_signatures(tok, off, P, kernel="direct")
+    assert int(sig_d.astype(np.uint64).sum()) == int(sig.astype(np.uint64).sum()) and np.array_equal(sig_d, sig)
+    # (4) no document of 256 uniform tokens keeps the empty value; minima are small as order statistics predict
+    assert (sig != 0xFFFFFFFF).all() and float(sig.mean()) < 2 ** 32 / 200
