@@ -12,6 +12,7 @@ _native.load()  # fail loudly if the CUDA library is absent
 from .hashfunc import sha1_hash32, sha1_hash64  # noqa: E402
 from .minhash import MinHash  # noqa: E402
 from .lean_minhash import LeanMinHash  # noqa: E402
+from .b_bit_minhash import bBitMinHash  # noqa: E402
 from .weighted_minhash import WeightedMinHash, WeightedMinHashGenerator  # noqa: E402
 from .lsh import GpuLSH, MinHashLSH, MinHashLSHDeletionSession, MinHashLSHInsertionSession  # noqa: E402
 from . import codec, engine  # noqa: E402
@@ -20,5 +21,5 @@ from . import codec, engine  # noqa: E402
 WeightedMinHashLSH = MinHashLSH
 
 __version__ = "0.1.0"
-__all__ = ["MinHash", "LeanMinHash", "WeightedMinHash", "WeightedMinHashGenerator", "MinHashLSH", "GpuLSH",
+__all__ = ["MinHash", "LeanMinHash", "bBitMinHash", "WeightedMinHash", "WeightedMinHashGenerator", "MinHashLSH", "GpuLSH",
            "WeightedMinHashLSH", "MinHashLSHInsertionSession", "MinHashLSHDeletionSession", "sha1_hash32", "sha1_hash64", "engine", "codec"]

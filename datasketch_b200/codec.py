@@ -155,3 +155,43 @@ def jaccard_topk(queries, db, topk: int = 10, self_base: int = -1, to_host: bool
         return cnt, idx
     c = cnt.cpu().numpy()
     return np.where(c >= 0, c, 0).astype(np.float64) / float(k), idx.cpu().numpy()
+
+
+def _bbit_geometry(num_perm: int, b: int):
+    if b < 0 or b > 32:
+        raise ValueError("b must be an integer in [0, 32]")
+    slot = 1 if b == 1 else 2 if b == 2 else 4 if b <= 4 else 8 if b <= 8 else 16 if b <= 16 else 32
+    per = 64 // slot
+    return slot, per, -(-num_perm // per)
+
+
+def bbit_pack(sig, b: int, stream=None):
+    """[N, K] u32 signatures -> [N, ceil(K / (64/slot))] int64 tensor holding the uint64 blocks a
+    ``bBitMinHash`` pickles (datasketch/b_bit_minhash.py:78-92), for every row at once."""
+    torch = _torch()
+    d_sig, is64 = _as_device_sig(sig)
+    if is64:
+        raise TypeError("bbit_pack takes the 32-bit signature matrix")
+    n, k = d_sig.shape
+    _, _, nblk = _bbit_geometry(k, b)
+    out = torch.empty((n, nblk), dtype=torch.int64, device=d_sig.device)
+    with torch.cuda.device(d_sig.device):
+        nv.check(nv.load().dsk_bbit_pack(d_sig.data_ptr(), n, k, int(b), out.data_ptr(), _stream(d_sig, stream)))
+    return out
+
+
+def bbit_unpack(blocks, num_perm: int, b: int, stream=None):
+    """Inverse of :func:`bbit_pack`: [N, nblocks] uint64 blocks -> [N, K] masked values (int32 storage)."""
+    torch = _torch()
+    if isinstance(blocks, np.ndarray):
+        nv.require_device(0)
+        blocks = torch.from_numpy(np.ascontiguousarray(blocks).view(np.int64)).cuda()
+    blocks = blocks.contiguous()
+    _, _, nblk = _bbit_geometry(num_perm, b)
+    if blocks.dim() != 2 or blocks.shape[1] != nblk:
+        raise ValueError("block matrix does not match num_perm / b")
+    out = torch.empty((blocks.shape[0], num_perm), dtype=torch.int32, device=blocks.device)
+    with torch.cuda.device(blocks.device):
+        nv.check(nv.load().dsk_bbit_unpack(blocks.data_ptr(), blocks.shape[0], num_perm, int(b), out.data_ptr(),
+                                           _stream(blocks, stream)))
+    return out

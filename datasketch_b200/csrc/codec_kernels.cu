@@ -209,6 +209,56 @@ __global__ void __launch_bounds__(256) band_fingerprint_kernel(const uint32_t *_
     }
 }
 
+// ---- b-bit MinHash blocks (datasketch/b_bit_minhash.py:78-92) ----------------------------------------
+// block i of a row packs values [i*n, (i+1)*n) masked to b bits, value j at bit (n-1-j)*slot; n = 64/slot.
+__global__ void __launch_bounds__(256) bbit_pack_kernel(const uint32_t *__restrict__ sig, int64_t n_rows, int k,
+                                                        uint32_t bmask, int slot, int nblk,
+                                                        uint64_t *__restrict__ out) {
+    const int per = 64 / slot;
+    const int64_t total = n_rows * nblk, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t row = e / nblk;
+        const int blk = (int)(e - row * nblk);
+        const uint32_t *v = sig + row * k + (int64_t)blk * per;
+        const int cnt = min(per, k - blk * per);
+        uint64_t w = 0;
+        for (int j = 0; j < cnt; ++j) w |= (uint64_t)(v[j] & bmask) << ((per - 1 - j) * slot);
+        out[e] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256) bbit_unpack_kernel(const uint64_t *__restrict__ blocks, int64_t n_rows, int k,
+                                                          int slot, int nblk, uint32_t *__restrict__ sig) {
+    const int per = 64 / slot;
+    const uint64_t mask = slot == 64 ? ~0ull : ((1ull << slot) - 1);
+    const int64_t total = n_rows * k, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t row = e / k;
+        const int c = (int)(e - row * k);
+        const int blk = c / per, j = c - blk * per;
+        sig[e] = (uint32_t)((blocks[row * nblk + blk] >> ((per - 1 - j) * slot)) & mask);
+    }
+}
+
+cudaError_t launch_bbit_pack(const uint32_t *sig, int64_t n, int k, int b, int slot, uint64_t *out, int sm_count,
+                             cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int per = 64 / slot, nblk = (k + per - 1) / per;
+    const uint32_t bmask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    const int grid = (int)std::min<int64_t>((n * nblk + 255) / 256, (int64_t)sm_count * 16);
+    bbit_pack_kernel<<<grid, 256, 0, s>>>(sig, n, k, bmask, slot, nblk, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bbit_unpack(const uint64_t *blocks, int64_t n, int k, int slot, uint32_t *sig, int sm_count,
+                               cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int per = 64 / slot, nblk = (k + per - 1) / per;
+    const int grid = (int)std::min<int64_t>((n * k + 255) / 256, (int64_t)sm_count * 16);
+    bbit_unpack_kernel<<<grid, 256, 0, s>>>(blocks, n, k, slot, nblk, sig);
+    return cudaGetLastError();
+}
+
 // ---- launchers --------------------------------------------------------------------------------------
 static void lean_header(int64_t seed, int k, int big_endian, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
     const uint32_t lo = (uint32_t)(uint64_t)seed, hi = (uint32_t)((uint64_t)seed >> 32);

@@ -662,6 +662,42 @@ int dsk_sha1_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64
     return DSK_OK;
 }
 
+static int bbit_slot(int b) {
+    if (b < 0 || b > 32) return -1;
+    if (b == 1) return 1;
+    if (b == 2) return 2;
+    if (b <= 4) return 4;
+    if (b <= 8) return 8;
+    if (b <= 16) return 16;
+    return 32;
+}
+
+int dsk_bbit_pack(const uint32_t *d_sig, int64_t n, int num_perm, int b, uint64_t *d_blocks, void *stream) {
+    const int slot = bbit_slot(b);
+    if (slot < 0 || n < 0 || num_perm <= 0 || (n > 0 && (!d_sig || !d_blocks))) {
+        set_error("dsk_bbit_pack: bad arguments (b must be in [0, 32])");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_bbit_pack(d_sig, n, num_perm, b, slot, d_blocks, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_bbit_unpack(const uint64_t *d_blocks, int64_t n, int num_perm, int b, uint32_t *d_sig, void *stream) {
+    const int slot = bbit_slot(b);
+    if (slot < 0 || n < 0 || num_perm <= 0 || (n > 0 && (!d_sig || !d_blocks))) {
+        set_error("dsk_bbit_unpack: bad arguments (b must be in [0, 32])");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_bbit_unpack(d_blocks, n, num_perm, slot, d_sig, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

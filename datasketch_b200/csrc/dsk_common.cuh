@@ -85,6 +85,11 @@ cudaError_t launch_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *d
 cudaError_t launch_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, void *out, int out_is_u64,
                                int sm_count, cudaStream_t s);
 
+cudaError_t launch_bbit_pack(const uint32_t *sig, int64_t n, int k, int b, int slot, uint64_t *out, int sm_count,
+                             cudaStream_t s);
+cudaError_t launch_bbit_unpack(const uint64_t *blocks, int64_t n, int k, int slot, uint32_t *sig, int sm_count,
+                               cudaStream_t s);
+
 // ---- PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -192,6 +192,14 @@ DSK_API int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_per
 DSK_API int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
                              int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *stream);
 
+/* ---- b-bit MinHash blocks ("next" row) -----------------------------------------
+ * bBitMinHash keeps the b lowest bits of each value (datasketch/b_bit_minhash.py:38) and packs
+ * them into 64-bit blocks, value j of a block at bit (n-1-j)*slot with slot = 1,2,4,8,16,32 >= b
+ * and n = 64/slot (:78-92).  d_blocks is [n, ceil(num_perm / n)] uint64 (the payload after the
+ * 21-byte '<qBdi' header of the pickle state). */
+DSK_API int dsk_bbit_pack(const uint32_t *d_sig, int64_t n, int num_perm, int b, uint64_t *d_blocks, void *stream);
+DSK_API int dsk_bbit_unpack(const uint64_t *d_blocks, int64_t n, int num_perm, int b, uint32_t *d_sig, void *stream);
+
 /* ---- default token hash on device ("next" row) --------------------------------
  * d_out[t] = sha1_hash32 (out_is_u64 = 0) or sha1_hash64 (= 1) of the byte string
  * d_bytes[d_byte_offsets[t] : d_byte_offsets[t+1]] -- datasketch/hashfunc.py:5-28, i.e. the

@@ -218,11 +218,35 @@ def gen_lsh():
     np.savez_compressed(os.path.join(OUT, "lsh.npz"), **d)
 
 
+def gen_bbit():
+    from datasketch.b_bit_minhash import bBitMinHash
+    d = {}
+    m = MinHash(num_perm=128, seed=1, hashfunc=ident)
+    for v in (11, 123, 92, 98, 123218, 32):
+        m.update(v)
+    m2 = MinHash(num_perm=128, seed=1, hashfunc=ident)
+    for v in (11, 123, 92, 98, 7, 32):
+        m2.update(v)
+    d["hv1"], d["hv2"] = m.hashvalues.copy(), m2.hashvalues.copy()
+    bs = [1, 2, 3, 4, 5, 8, 12, 16, 27, 32]
+    d["bs"] = np.array(bs, dtype=np.int64)
+    for b in bs:
+        x, y = bBitMinHash(m, b), bBitMinHash(m2, b)
+        d[f"state_b{b}"] = np.frombuffer(bytes(x.__getstate__()), dtype=np.uint8)
+        d[f"hv_b{b}"] = x.hashvalues.copy()
+        d[f"jac_b{b}"] = np.float64(x.jaccard(y))
+        d[f"size_b{b}"] = np.int64(x.bytesize())
+    xr, yr = bBitMinHash(m, 4, r=0.3), bBitMinHash(m2, 4, r=0.1)
+    d["jac_b4_r"] = np.float64(xr.jaccard(yr))
+    np.savez_compressed(os.path.join(OUT, "bbit.npz"), **d)
+
+
 if __name__ == "__main__":
     print("reference:", datasketch.__file__)
     gen_minhash()
     gen_lean()
     gen_wmh()
     gen_lsh()
+    gen_bbit()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
