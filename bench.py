@@ -409,6 +409,15 @@ def run_ours(args):
                          "note": "binding roof is the integer pipe (T*K evaluations/doc), see DESIGN.md"},
             "e2e": e2e, "gpu_launches": args.steps + e2e_launches, "clocks": clocks,
         }
+        # the roof that actually binds this kernel: one 32-bit IMAD per (token, permutation) evaluation is the floor
+        # of any exact scheme, and B200 issues IMAD at 16 lanes/clk/SMSP = 64 lanes/clk/SM (profiles/)
+        sm_count = nv.device_info(local)["sm_count"]
+        clk_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        evals_per_s = float(n) * t * k / (ms_step * 1e-3)
+        imad_peak = sm_count * 64 * clk_mhz * 1e6
+        line["int_pipe"] = {"bound": "imad (fmaheavy pipe)", "achieved": evals_per_s, "peak": imad_peak,
+                            "unit": "evaluations/s per GPU", "frac": evals_per_s / imad_peak,
+                            "note": "peak = SMs x 64 IMAD lanes/clk x SM clock under load; 1 IMAD per evaluation minimum"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if allgather is not None:

@@ -4,9 +4,10 @@
 // documents as MinHash.bulk does (:464-522).  See DESIGN.md "Kernel 1".
 //
 // Work decomposition
-//   warp  <-> a contiguous range of documents (token-balanced static partition of the CSR
-//             batch), streamed through a per-warp double-buffered shared-memory ring that
-//             is filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier), 2 KB per chunk.
+//   warp  <-> units of up to 32 consecutive documents pulled from a global atomic counter
+//             (dynamic distribution), streamed through a per-warp 3-slot shared-memory ring
+//             (previous | current | next) that is filled by 1-D TMA bulk copies
+//             (cp.async.bulk + mbarrier), 2 KB per chunk.
 //   lane  <-> P consecutive permutations (a_k, b_k live in registers); a 16-token block is
 //             read back from shared memory with four broadcast LDS.128.
 //
@@ -52,16 +53,6 @@ __device__ __forceinline__ uint32_t eval_exact(uint64_t a, uint64_t b, uint64_t 
     return (uint32_t)s;
 }
 
-// first d in [0, n] with off[d] >= v
-__device__ __forceinline__ int64_t lower_bound_i64(const int64_t *off, int64_t n, int64_t v) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (__ldg(off + mid) < v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 template <typename TokT> struct TokLoad;
 template <> struct TokLoad<uint32_t> {
     // 16 tokens = 4 x LDS.128 (all lanes read the same address: broadcast, 1 wavefront each)
@@ -99,8 +90,6 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
     __shared__ __align__(8) uint64_t s_bar[kWarps][kNBuf];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
-    const int64_t nw = (int64_t)gridDim.x * kWarps;
     const TokT *__restrict__ tokens = static_cast<const TokT *>(prm.tokens);
     const int64_t *__restrict__ offsets = prm.offsets;
     const int K = prm.k;
@@ -132,7 +121,6 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
     // ---- dynamic work distribution: warps pull units of `docs_per_unit` consecutive documents from a
     // global counter, so a warp the SM's arbiter favours simply takes more units and all warps finish
     // together (a static split left ~20 % of the warp slots empty in the tail).
-    (void)gw; (void)nw;
     while (true) {
     int64_t unit = 0;
     if (lane == 0) unit = (int64_t)atomicAdd(prm.work_counter + blockIdx.y, 1u);
