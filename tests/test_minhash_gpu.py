@@ -287,3 +287,44 @@ def test_full_size_c2_properties(dsk):
     assert int(sig_d.astype(np.uint64).sum()) == int(sig.astype(np.uint64).sum()) and np.array_equal(sig_d, sig)
     # (4) no document of 256 uniform tokens keeps the empty value; minima are small as order statistics predict
     assert (sig != 0xFFFFFFFF).all() and float(sig.mean()) < 2 ** 32 / 200
+
+
+def test_api_fuzz_against_oracle(dsk):
+    """Random sequences of update / update_batch / merge / copy / clear / union / LeanMinHash on MinHash objects
+    (lazy queue + GPU flush) tracked step by step against the numpy oracle."""
+    rs = np.random.RandomState(77)
+    for k, seed in [(128, 1), (33, 5), (256, 9)]:
+        P = o.init_permutations(k, seed)
+        objs = [dsk.MinHash(num_perm=k, seed=seed, hashfunc=int) for _ in range(4)]
+        refs = [o.init_hashvalues(k) for _ in range(4)]
+        for step in range(120):
+            i, j = rs.randint(0, 4), rs.randint(0, 4)
+            op = rs.randint(0, 8)
+            if op == 0:
+                v = int(rs.randint(0, 2 ** 32, dtype=np.uint64))
+                objs[i].update(v)
+                refs[i] = o.update_one(refs[i], v, P)
+            elif op in (1, 2):
+                vals = [int(x) for x in rs.randint(0, 2 ** 32 if op == 1 else 50, size=rs.randint(0, 40), dtype=np.uint64)]
+                objs[i].update_batch(vals)
+                refs[i] = o.update_batch(refs[i], vals, P)
+            elif op == 3 and i != j:
+                objs[i].merge(objs[j])
+                refs[i] = o.merge(refs[i], refs[j])
+            elif op == 4:
+                objs[i] = objs[j].copy()
+                refs[i] = refs[j].copy()
+            elif op == 5 and rs.rand() < 0.3:
+                objs[i].clear()
+                refs[i] = o.init_hashvalues(k)
+            elif op == 6:
+                u = dsk.MinHash.union(objs[i], objs[j])
+                assert np.array_equal(u.hashvalues, np.minimum(refs[i], refs[j]))
+                assert dsk.LeanMinHash(u).jaccard(dsk.LeanMinHash(objs[i])) == o.jaccard(np.minimum(refs[i], refs[j]), refs[i])
+            else:
+                assert objs[i].jaccard(objs[j]) == o.jaccard(refs[i], refs[j])
+                assert objs[i].is_empty() == bool((refs[i] == 0xFFFFFFFF).all())
+            if step % 7 == 0:
+                assert np.array_equal(objs[i].hashvalues, refs[i]) and objs[i].hashvalues.dtype == np.uint64
+        for a, b in zip(objs, refs):
+            assert np.array_equal(a.hashvalues, b) and len(a) == k
