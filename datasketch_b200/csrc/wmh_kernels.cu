@@ -64,8 +64,35 @@ __global__ void __launch_bounds__(kWmhThreads) wmh_kernel(const WmhParams p) {
                 const float *rp = p.rs_t + (int64_t)d0 * p.ss_pad + s;
                 const float *cp = p.lncs_t + (int64_t)d0 * p.ss_pad + s;
                 const float *bp = p.betas_t + (int64_t)d0 * p.ss_pad + s;
-#pragma unroll 2
-                for (int dd = 0; dd < nd; ++dd) {
+                // kUnrollD dims per trip: all 3*kUnrollD parameter loads (L2-resident, ~500 cycles) are issued
+                // before the first evaluation, so their latency overlaps kUnrollD*kVec evaluations
+                constexpr int kUnrollD = 4;
+                int dd = 0;
+                for (; dd + kUnrollD <= nd; dd += kUnrollD) {
+                    float r[kUnrollD], lc[kUnrollD], be[kUnrollD];
+#pragma unroll
+                    for (int q = 0; q < kUnrollD; ++q) {
+                        r[q] = __ldg(rp + (int64_t)(dd + q) * p.ss_pad);
+                        lc[q] = __ldg(cp + (int64_t)(dd + q) * p.ss_pad);
+                        be[q] = __ldg(bp + (int64_t)(dd + q) * p.ss_pad);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kUnrollD; ++q) {
+                        const float4 x0 = *reinterpret_cast<const float4 *>(&s_vlog[dd + q][0]);
+                        const float4 x1 = *reinterpret_cast<const float4 *>(&s_vlog[dd + q][4]);
+                        const float xs[kVec] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                        for (int u = 0; u < kVec; ++u) {
+                            const float t = floorf(__fadd_rn(__fdiv_rn(xs[u], r[q]), be[q]));
+                            const float ln_y = __fmul_rn(__fsub_rn(t, be[q]), r[q]);
+                            const float ln_a = __fsub_rn(__fsub_rn(lc[q], ln_y), r[q]);
+                            if (ln_a < best[u] || (bk[u] < 0 && ln_a == ln_a)) {  // NaN never wins; first index kept on ties
+                                best[u] = ln_a; bk[u] = d0 + dd + q; bt[u] = t;
+                            }
+                        }
+                    }
+                }
+                for (; dd < nd; ++dd) {
                     const float r = __ldg(rp + (int64_t)dd * p.ss_pad);
                     const float lc = __ldg(cp + (int64_t)dd * p.ss_pad);
                     const float be = __ldg(bp + (int64_t)dd * p.ss_pad);
@@ -77,7 +104,7 @@ __global__ void __launch_bounds__(kWmhThreads) wmh_kernel(const WmhParams p) {
                         const float t = floorf(__fadd_rn(__fdiv_rn(xs[u], r), be));
                         const float ln_y = __fmul_rn(__fsub_rn(t, be), r);
                         const float ln_a = __fsub_rn(__fsub_rn(lc, ln_y), r);
-                        if (ln_a < best[u] || (bk[u] < 0 && ln_a == ln_a)) {  // NaN never wins; first index kept on ties
+                        if (ln_a < best[u] || (bk[u] < 0 && ln_a == ln_a)) {
                             best[u] = ln_a; bk[u] = d0 + dd; bt[u] = t;
                         }
                     }
