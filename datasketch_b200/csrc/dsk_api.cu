@@ -698,6 +698,21 @@ int dsk_bbit_unpack(const uint64_t *d_blocks, int64_t n, int num_perm, int b, ui
     return DSK_OK;
 }
 
+int dsk_forest_query(const uint32_t *d_sig, const int32_t *d_order, int64_t n, int num_perm, int l, int k,
+                     const uint32_t *d_qsig, int64_t nq, int topk, int32_t *d_out, void *stream) {
+    if (n < 0 || nq < 0 || num_perm <= 0 || l <= 0 || k <= 0 || (int64_t)l * k > num_perm || topk <= 0 || topk > 1024 ||
+        (nq > 0 && (!d_qsig || !d_out)) || (n > 0 && (!d_sig || !d_order))) {
+        set_error("dsk_forest_query: bad arguments (need l*k <= num_perm, 0 < topk <= 1024)");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_forest_query(d_sig, d_order, n, num_perm, l, k, d_qsig, nq, topk, d_out, dev->sm_count,
+                                 (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

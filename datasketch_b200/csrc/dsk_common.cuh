@@ -90,6 +90,10 @@ cudaError_t launch_bbit_pack(const uint32_t *sig, int64_t n, int k, int b, int s
 cudaError_t launch_bbit_unpack(const uint64_t *blocks, int64_t n, int k, int slot, uint32_t *sig, int sm_count,
                                cudaStream_t s);
 
+cudaError_t launch_forest_query(const uint32_t *sig, const int32_t *order, int64_t n, int K, int l, int k,
+                                const uint32_t *qsig, int64_t nq, int topk, int32_t *out, int sm_count,
+                                cudaStream_t s);
+
 // ---- PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -195,3 +195,88 @@ cudaError_t launch_exclusive_scan(const int64_t *in, int64_t n, int64_t *out, in
 }
 
 }  // namespace dsk
+
+// ---- LSH Forest query (datasketch/lshforest.py:74-128) --------------------------------------------------
+// order[tree][pos] = document numbers sorted by (the tree's k-tuple, document number); the sorted list of
+// distinct keys + per-key insertion-ordered buckets of the reference flatten to exactly this sequence.
+// warp <-> query.  For each prefix length r = k..1: lanes binary-search the l trees in parallel (tuple compare
+// on the signatures themselves), then the matches are emitted tree by tree, in sequence order, into the
+// query's result list (first `topk` DISTINCT documents), stopping exactly where the reference returns.
+namespace dsk {
+
+__device__ __forceinline__ int lex_cmp(const uint32_t *a, const uint32_t *b, int r) {
+    for (int q = 0; q < r; ++q) {
+        const uint32_t x = a[q], y = b[q];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) forest_query_kernel(const uint32_t *__restrict__ sig,
+                                                           const int32_t *__restrict__ order, int64_t n, int K, int l,
+                                                           int k, const uint32_t *__restrict__ qsig, int64_t nq,
+                                                           int topk, int32_t *__restrict__ out) {
+    extern __shared__ int32_t s_res[];  // [warps][topk]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t *res = s_res + warp * topk;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; q < nq; q += warps) {
+        const uint32_t *qrow = qsig + q * K;
+        int cnt = 0;
+        bool done = false;
+        for (int r = k; r >= 1 && !done; --r) {
+            for (int t0 = 0; t0 < l && !done; t0 += 32) {
+                const int tree = t0 + lane;
+                int64_t lo = 0;
+                if (tree < l) {  // lower bound of the r-prefix in this lane's tree
+                    const uint32_t *qt = qrow + tree * k;
+                    const int32_t *ord = order + (int64_t)tree * n;
+                    int64_t hi = n;
+                    while (lo < hi) {
+                        const int64_t mid = lo + ((hi - lo) >> 1);
+                        if (lex_cmp(sig + (int64_t)ord[mid] * K + tree * k, qt, r) < 0) lo = mid + 1;
+                        else hi = mid;
+                    }
+                }
+                const int ntree = min(32, l - t0);
+                for (int j = 0; j < ntree && !done; ++j) {  // emit in tree order; lane 0 owns the result list
+                    int64_t pos = __shfl_sync(0xFFFFFFFFu, lo, j);
+                    if (lane == 0) {
+                        const int tj = t0 + j;
+                        const uint32_t *qt = qrow + tj * k;
+                        const int32_t *ord = order + (int64_t)tj * n;
+                        while (pos < n) {
+                            const int32_t d = ord[pos];
+                            if (lex_cmp(sig + (int64_t)d * K + tj * k, qt, r) != 0) break;
+                            bool seen = false;
+                            for (int e = 0; e < cnt; ++e) seen = seen || (res[e] == d);
+                            if (!seen) {
+                                res[cnt++] = d;
+                                if (cnt >= topk) break;
+                            }
+                            ++pos;
+                        }
+                    }
+                    cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0);
+                    done = cnt >= topk;
+                }
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < topk; e += 32) out[q * topk + e] = e < cnt ? res[e] : -1;
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_forest_query(const uint32_t *sig, const int32_t *order, int64_t n, int K, int l, int k,
+                                const uint32_t *qsig, int64_t nq, int topk, int32_t *out, int sm_count,
+                                cudaStream_t s) {
+    if (nq <= 0) return cudaSuccess;
+    int64_t grid = (nq + 3) / 4;
+    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+    const size_t smem = (size_t)4 * topk * sizeof(int32_t);
+    forest_query_kernel<<<(unsigned)grid, 128, smem, s>>>(sig, order, n, K, l, k, qsig, nq, topk, out);
+    return cudaGetLastError();
+}
+
+}  // namespace dsk

@@ -192,6 +192,15 @@ DSK_API int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_per
 DSK_API int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
                              int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *stream);
 
+/* ---- LSH Forest query ("next" row) ----------------------------------------------
+ * d_order is [l, n] int32: for tree t, the document numbers sorted by (sig[doc][t*k:(t+1)*k]
+ * lexicographically, document number) -- the flattening of the reference's sorted key list +
+ * insertion-ordered buckets (datasketch/lshforest.py:68-72).  For each query the kernel walks
+ * prefix lengths r = k..1 and trees 0..l-1 exactly like MinHashLSHForest.query (:74-128) and writes
+ * the first `topk` (<= 1024) distinct document numbers it meets (d_out [nq, topk], -1 pads). */
+DSK_API int dsk_forest_query(const uint32_t *d_sig, const int32_t *d_order, int64_t n, int num_perm, int l, int k,
+                             const uint32_t *d_qsig, int64_t nq, int topk, int32_t *d_out, void *stream);
+
 /* ---- b-bit MinHash blocks ("next" row) -----------------------------------------
  * bBitMinHash keeps the b lowest bits of each value (datasketch/b_bit_minhash.py:38) and packs
  * them into 64-bit blocks, value j of a block at bit (n-1-j)*slot with slot = 1,2,4,8,16,32 >= b

@@ -241,6 +241,30 @@ def gen_bbit():
     np.savez_compressed(os.path.join(OUT, "bbit.npz"), **d)
 
 
+def gen_forest():
+    """MinHashLSHForest.query results (as sorted id lists) on the lsh.npz signatures, several (l, k)."""
+    from datasketch import MinHashLSHForest
+    sig = np.load(os.path.join(OUT, "lsh.npz"))["sig"]
+    d = {}
+    for l in (8, 32):
+        f = MinHashLSHForest(num_perm=128, l=l)
+        for i, row in enumerate(sig):
+            f.add(i, LeanMinHash(seed=1, hashvalues=row.astype(np.uint64)))
+        f.index()
+        for topk in (1, 5, 20):
+            res, ptr = [], [0]
+            for row in sig[:120]:
+                r = sorted(f.query(LeanMinHash(seed=1, hashvalues=row.astype(np.uint64)), topk))
+                res.extend(r)
+                ptr.append(len(res))
+            d[f"l{l}_k{topk}_idx"] = np.array(res, dtype=np.int64)
+            d[f"l{l}_k{topk}_ptr"] = np.array(ptr, dtype=np.int64)
+        if l == 8:
+            d["keys_doc0"] = np.frombuffer(b"".join(f.keys[0]), dtype=np.uint8)
+            d["hashvalues_doc3"] = f.get_minhash_hashvalues(3)
+    np.savez_compressed(os.path.join(OUT, "forest.npz"), **d)
+
+
 if __name__ == "__main__":
     print("reference:", datasketch.__file__)
     gen_minhash()
@@ -248,5 +272,6 @@ if __name__ == "__main__":
     gen_wmh()
     gen_lsh()
     gen_bbit()
+    gen_forest()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
