@@ -112,7 +112,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -266,22 +266,35 @@ def run_ours(args):
         time.sleep(0.3)
 
     # ---- value: device-resident, CUDA events ----------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
+    BAD = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        tt = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
+
+    def timed_value():
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        barrier()
+        tw0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+        tw1 = time.perf_counter()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, tw0, tw1
+
+    ms_total, t_wall0, t_wall1 = timed_value()
+    remeasured = False
+    if rank == 0 and world == 1:
+        time.sleep(0.05)
+        first = sampler.summary(t_wall0, t_wall1)
+        if BAD & set(first["reasons"]):      # thermal / hw slowdown seen: re-measure once (timing rules)
+            ms_total, t_wall0, t_wall1 = timed_value()
+            remeasured = True
     ms_step = ms_total / args.steps
     value = n * world / (ms_step * 1e-3)
 
@@ -376,6 +389,13 @@ def run_ours(args):
     if rank == 0:
         sampler.stop()
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+    if clocks is not None:
+        clocks["remeasured"] = remeasured
+        if clocks["samples"] < 3:   # the timed region is only tens of ms: add the samples of the whole run under load
+            wide = sampler.summary(t_wall0 - 0.2, time.perf_counter())
+            clocks["sm_mhz_whole_run"] = wide["sm_mhz"]
+            clocks["reasons"] = sorted(set(clocks["reasons"]) | set(wide["reasons"]))
+            clocks["samples_whole_run"] = wide["samples"]
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
