@@ -193,6 +193,54 @@ class ShardedLSH:
         return ptr, out
 
 
+def gather_signature_blocks(sig_local, group=None):
+    """All-gather per-rank [n_r, K] signature blocks (possibly of different heights) into the full
+    [sum n_r, K] matrix in rank order, on every rank.  Returns ``(full, base, counts)`` where ``base`` is this
+    rank's first global row.  This is the one exchange step of the path (see module docstring)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_me = int(sig_local.shape[0])
+    if world == 1:
+        return sig_local, 0, [n_me]
+    dev = sig_local.device
+    t = torch.tensor([n_me], dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allc, t, group=group)
+    counts = [int(x.item()) for x in allc]
+    rows = max(max(counts), 1)
+    if min(counts) == rows:
+        padded = sig_local.contiguous()
+    else:
+        padded = torch.zeros((rows, sig_local.shape[1]), dtype=sig_local.dtype, device=dev)
+        padded[:n_me] = sig_local
+    gathered = torch.empty((world * rows, sig_local.shape[1]), dtype=sig_local.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    if min(counts) == rows:
+        full = gathered
+    else:
+        full = torch.cat([gathered[r * rows: r * rows + counts[r]] for r in range(world)])
+    return full, sum(counts[:rank]), counts
+
+
+def sharded_jaccard_topk(sig_local, topk: int = 10, group=None, topk_fn: Optional[Callable] = None):
+    """All-pairs top-k Jaccard over signatures sharded across ranks (config C5).
+
+    Every rank all-gathers the signature matrix, then ranks the *whole* corpus for its own rows only
+    (``dsk_jaccard_topk`` with ``self_base`` = its first global row, so a row never lists itself):
+    the quadratic work splits evenly and the answers need no second exchange.  Returns
+    ``(count int32 [n_local, topk], index int64 [n_local, topk])`` device tensors with global row
+    numbers; count / K is the reference's ``jaccard`` (datasketch/minhash.py:324).
+
+    ``topk_fn(queries, db, topk, self_base)`` exists for the CPU/gloo tests; default = the GPU kernel."""
+    full, base, _ = gather_signature_blocks(sig_local, group)
+    if topk_fn is None:
+        from . import codec
+        return codec.jaccard_topk(sig_local, full, topk=topk, self_base=base, to_host=False)
+    return topk_fn(sig_local, full, topk, base)
+
+
 class FusedGather:
     """Signature build fused with the all-gather (NVLink peer stores instead of a separate NCCL pass).
 

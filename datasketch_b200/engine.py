@@ -121,19 +121,28 @@ def bulk_signatures_device(d_tokens, d_offsets, n_tokens: int, permutations: np.
     return d_out
 
 
-def sha1_hash_tokens_device(flat_tokens, device: int = 0, out_u64: bool = False):
-    """Device-side ``sha1_hash32`` / ``sha1_hash64`` (datasketch/hashfunc.py:5-28) of a flat list of
-    byte strings -> CUDA tensor of hashes (int32 / int64 storage of the unsigned values)."""
+_stage: dict = {}
+
+
+def _pinned_stage(name: str, nbytes: int):
+    """Grow-only pinned host staging buffer (uint8 tensor), one per purpose per process."""
+    import torch
+    t = _stage.get(name)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty((max(int(nbytes) * 2, 1 << 24) + 7) // 8 * 8, dtype=torch.uint8, pin_memory=True)
+        _stage[name] = t
+    return t
+
+
+def _sha1_blob_device(blob, boff: np.ndarray, n: int, device: int = 0, out_u64: bool = False):
+    """SHA1-32/64 of ``n`` byte strings stored back to back in ``blob`` (``boff`` = n+1 byte offsets)."""
     import torch
     nv.require_device(device)
-    n = len(flat_tokens)
-    lens = np.fromiter(map(len, flat_tokens), dtype=np.int64, count=n)
-    blob = b"".join(flat_tokens)  # TypeError for non-bytes tokens, like hashlib would raise
-    boff = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lens, out=boff[1:])
     dev = torch.device("cuda", device)
-    d_bytes = (torch.frombuffer(bytearray(blob), dtype=torch.uint8) if blob else torch.zeros(1, dtype=torch.uint8)).to(dev)
-    d_boff = torch.from_numpy(boff).to(dev)
+    if not isinstance(blob, bytearray):
+        blob = bytearray(blob)  # torch.frombuffer wants a writable buffer
+    d_bytes = (torch.frombuffer(blob, dtype=torch.uint8) if len(blob) else torch.zeros(1, dtype=torch.uint8)).to(dev)
+    d_boff = torch.from_numpy(np.ascontiguousarray(boff, dtype=np.int64)).to(dev)
     out = torch.empty((max(n, 4),), dtype=torch.int64 if out_u64 else torch.int32, device=dev)
     with torch.cuda.device(device):
         nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n, out.data_ptr(), int(out_u64),
@@ -141,20 +150,67 @@ def sha1_hash_tokens_device(flat_tokens, device: int = 0, out_u64: bool = False)
     return out[:n] if n >= 4 else out
 
 
+def sha1_hash_tokens_device(flat_tokens, device: int = 0, out_u64: bool = False):
+    """Device-side ``sha1_hash32`` / ``sha1_hash64`` (datasketch/hashfunc.py:5-28) of a flat list of
+    byte strings -> CUDA tensor of hashes (int32 / int64 storage of the unsigned values)."""
+    n = len(flat_tokens)
+    lens = np.fromiter(map(len, flat_tokens), dtype=np.int64, count=n)
+    blob = b"".join(flat_tokens)  # TypeError for non-bytes tokens, like hashlib would raise
+    boff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=boff[1:])
+    if int(boff[-1]) != len(blob):
+        raise TypeError("tokens must be byte strings (item size 1)")
+    return _sha1_blob_device(blob, boff, n, device, out_u64)
+
+
 def bulk_signatures_sha1(docs: Sequence[Sequence[bytes]], permutations: np.ndarray, init: Optional[np.ndarray] = None,
                          device: int = 0) -> np.ndarray:
     """``MinHash.bulk`` for byte tokens under the DEFAULT hash function, entirely on device:
     SHA1-32 of every token (``dsk_sha1_tokens``) feeds the signature kernel without the hashes ever
-    visiting the host.  Returns the [N, K] uint64 matrix (the reference's dtype)."""
+    visiting the host.  Returns the [N, K] uint64 matrix (the reference's dtype).
+
+    Host packing is one C-level pass per document (``bytes.join`` while the document's tokens are
+    cache-hot) plus one ``map(len, ...)`` over all tokens; a token that is not bytes-like raises
+    TypeError before anything reaches the device (the caller then takes the per-token hashfunc
+    route, which raises what the reference raises)."""
+    import itertools
     import torch
+    nv.require_device(device)
+    dev = torch.device("cuda", device)
     n = len(docs)
     doc_lens = np.fromiter(map(len, docs), dtype=np.int64, count=n)
     off = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(doc_lens, out=off[1:])
-    flat = [t for d in docs for t in d]
-    n_tok = len(flat)
-    d_hash = sha1_hash_tokens_device(flat, device)
-    dev = d_hash.device
+    n_tok = int(off[-1])
+    lens = np.fromiter(map(len, itertools.chain.from_iterable(docs)), dtype=np.int64, count=n_tok)
+    # grow-only pinned staging (no fresh-page faults per call, full-rate H2D); safe to reuse because this
+    # function returns only after the device->host copy of the result, which is ordered after both uploads
+    h_boff = _pinned_stage("boff", (n_tok + 1) * 8).view(torch.int64).numpy()
+    h_boff[0] = 0
+    np.cumsum(lens, out=h_boff[1:n_tok + 1])
+    total = int(h_boff[n_tok])
+    h_blob = _pinned_stage("blob", total)
+    mv = memoryview(h_blob.numpy())
+    pos = 0
+    for d in docs:
+        piece = b"".join(d)  # TypeError for a token that is not bytes-like
+        end = pos + len(piece)
+        if end > total:
+            break
+        mv[pos:end] = piece
+        pos = end
+    else:
+        end = pos
+    if end != total:  # e.g. array('I') tokens: len() counts items, not bytes
+        raise TypeError("tokens must be byte strings (item size 1)")
+    d_bytes = torch.empty((max(total, 1),), dtype=torch.uint8, device=dev)
+    d_bytes[:total].copy_(h_blob[:total], non_blocking=True)
+    d_boff = torch.empty((n_tok + 1,), dtype=torch.int64, device=dev)
+    d_boff.copy_(_pinned_stage("boff", 0).view(torch.int64)[:n_tok + 1], non_blocking=True)
+    d_hash = torch.empty((max(n_tok, 4),), dtype=torch.int32, device=dev)
+    with torch.cuda.device(device):
+        nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, d_hash.data_ptr(), 0,
+                                            torch.cuda.current_stream(dev).cuda_stream))
     d_off = torch.from_numpy(off).to(dev)
     d_out = torch.empty((n, permutations.shape[1]), dtype=torch.int64, device=dev)
     d_init, stride = None, 0

@@ -17,6 +17,7 @@ for ``gpu_mode='always'`` (minhash.py:272-274).
 from __future__ import annotations
 
 import copy
+import gc
 import warnings
 from typing import Callable, Generator, Iterable, List, Optional
 
@@ -211,36 +212,41 @@ class MinHash:
         proto = cls(**minhash_kwargs)
         perms = np.ascontiguousarray(np.asarray(proto.permutations, dtype=np.uint64))
         hf = proto.hashfunc
-        batch: List[List[int]] = []
+        batch: list = []
 
         # With the reference's default hash function on byte tokens, hashing moves to the device too
         # (dsk_sha1_tokens): same values as hashfunc.sha1_hash32, no per-token Python hashlib call.
         device_sha1 = hf is sha1_hash32
 
-        def run(docs, hashed):
+        def run(docs):
             init = proto.hashvalues if not proto.is_empty() else None
-            if hashed:
-                tok, off = engine.pack_docs(docs)
+            sig = None
+            if device_sha1:
+                try:
+                    sig = engine.bulk_signatures_sha1(docs, perms, init=init)
+                except TypeError:
+                    sig = None  # a non-bytes token: the per-token route below raises what the reference raises
+            if sig is None:
+                tok, off = engine.pack_docs([[hf(t) for t in d] for d in docs])
                 sig = engine.bulk_signatures(tok, off, perms, init=init, out_u64=True)
-            else:
-                sig = engine.bulk_signatures_sha1(docs, perms, init=init)
-            for row in sig:
-                yield cls._from_row(proto, row.copy())
+            # One object per row.  The cyclic GC is paused for the burst: tens of thousands of fresh container
+            # objects would otherwise trigger full collections that re-traverse the caller's (large) corpus.
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                out = [cls._from_row(proto, row.copy()) for row in sig]
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            yield from out
 
-        raw_ok = device_sha1
         for doc in b:
-            doc = doc if isinstance(doc, (list, tuple)) else list(doc)
-            if raw_ok and not all(isinstance(t, (bytes, bytearray)) for t in doc):
-                # a non-bytes token: fall back to calling the hash function per token (it will raise as usual)
-                batch = [[hf(t) for t in d] for d in batch]
-                raw_ok = False
-            batch.append(doc if raw_ok else [hf(t) for t in doc])
+            batch.append(doc if isinstance(doc, (list, tuple)) else list(doc))
             if len(batch) >= batch_docs:
-                yield from run(batch, hashed=not raw_ok)
+                yield from run(batch)
                 batch = []
-                raw_ok = device_sha1
         if batch:
-            yield from run(batch, hashed=not raw_ok)
+            yield from run(batch)
 
     # -- pickling: only host state travels (cf. minhash.py:529-537) ---------------------------------
     def __getstate__(self):

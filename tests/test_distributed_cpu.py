@@ -130,3 +130,48 @@ def test_sharded_lsh_gloo_world2():
         assert ptr[0] == 0 and ptr[-1] == len(idx)
         for j, qi in enumerate(qsel):
             assert sorted(idx[ptr[j]:ptr[j + 1]].tolist()) == sorted(ref.query(sig[qi].astype(np.uint64)))
+
+
+def _np_topk(q, db, topk, self_base):
+    """Checker for all-pairs top-k: count of equal positions, best first, ties -> lower index."""
+    qn, dbn = q.numpy().view(np.uint32), db.numpy().view(np.uint32)
+    out_c = np.full((len(qn), topk), -1, np.int32)
+    out_i = np.full((len(qn), topk), -1, np.int64)
+    for i, row in enumerate(qn):
+        cnt = (dbn == row[None, :]).sum(axis=1).astype(np.int64)
+        order = np.lexsort((np.arange(len(dbn)), -cnt))
+        order = order[order != self_base + i][:topk]
+        out_c[i, :len(order)] = cnt[order]
+        out_i[i, :len(order)] = order
+    return torch.from_numpy(out_c), torch.from_numpy(out_i)
+
+
+def _topk_worker(rank, world, port, sig, cut, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datasketch_b200.distributed import gather_signature_blocks, sharded_jaccard_topk
+    mine = torch.from_numpy(sig[cut[rank]:cut[rank + 1]].view(np.int32).copy())
+    full, base, counts = gather_signature_blocks(mine)
+    assert base == cut[rank] and counts == [cut[1] - cut[0], cut[2] - cut[1]]
+    assert np.array_equal(full.numpy().view(np.uint32), sig)
+    cnt, idx = sharded_jaccard_topk(mine, topk=5, topk_fn=_np_topk)
+    ret[rank] = (cnt.numpy().copy(), idx.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cut", [[0, 90, 200], [0, 100, 200]])       # uneven (padded gather) and even shards
+def test_sharded_jaccard_topk_gloo_world2(cut):
+    rs = np.random.RandomState(11)
+    n, k = 200, 32
+    sig = rs.randint(0, 3, size=(n, k)).astype(np.uint32)
+    sig[rs.randint(0, n, 30)] = sig[rs.randint(0, n, 30)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_topk_worker, args=(2, _free_port(), sig, cut, ret), nprocs=2, join=True)
+    full = torch.from_numpy(sig.view(np.int32))
+    wc, wi = _np_topk(full, full, 5, 0)                              # single-process answer over the whole corpus
+    got_c = np.concatenate([ret[0][0], ret[1][0]])
+    got_i = np.concatenate([ret[0][1], ret[1][1]])
+    assert np.array_equal(got_c, wc.numpy()) and np.array_equal(got_i, wi.numpy())

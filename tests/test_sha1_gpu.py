@@ -45,3 +45,31 @@ def test_bulk_default_hashfunc_bytes_tokens(dsk, golden):
         assert np.array_equal(ref.hashvalues, m.hashvalues)
     with pytest.raises(TypeError):
         dsk.MinHash.bulk([["not-bytes"]], num_perm=4)      # hashlib raises TypeError for str, so do we
+
+
+def test_bulk_bytes_like_tokens_and_batches(dsk):
+    """bytearray / memoryview tokens, generator documents, several device batches, and a token type
+    whose len() is not its byte size (falls back to the per-token hash function): all rows must equal
+    the per-document update_batch result."""
+    import array
+    rs = np.random.RandomState(5)
+    raw = [[bytes(rs.randint(0, 256, size=rs.randint(0, 40)).astype(np.uint8)) for _ in range(rs.randint(0, 30))]
+           for _ in range(300)]
+    docs = []
+    for i, d in enumerate(raw):
+        if i % 3 == 0:
+            docs.append([bytearray(t) for t in d])
+        elif i % 3 == 1:
+            docs.append(memoryview(t) for t in d)          # a generator of memoryviews
+        else:
+            docs.append(tuple(d))
+    ms = list(dsk.MinHash.generator(docs, batch_docs=64, num_perm=64, seed=3))
+    assert len(ms) == len(raw)
+    perms = o.init_permutations(64, 3)
+    for d, m in zip(raw, ms):
+        want = o.update_batch(o.init_hashvalues(64), [o.sha1_hash32(t) for t in d], perms)
+        assert np.array_equal(m.hashvalues, want)
+    odd = [[array.array("I", [1, 2, 3]), b"abc"]]          # hashlib hashes the 12 raw bytes of the array
+    (m,) = dsk.MinHash.bulk(odd, num_perm=16, seed=2)
+    want = o.update_batch(o.init_hashvalues(16), [o.sha1_hash32(t) for t in odd[0]], o.init_permutations(16, 2))
+    assert np.array_equal(m.hashvalues, want)
