@@ -335,6 +335,33 @@ def run_ours(args):
                "d2h_bytes_per_step": int(h_out.nbytes) * world, "ms_per_step": dt / args.steps * 1e3}
         if rank == 0 and not np.array_equal(h_out[idx], want):
             raise SystemExit("bench: host-path signatures differ from the oracle -- number is invalid")
+        # the e2e leg's own roofline: the same bytes as bare pinned copies, both directions at once (PCIe duplex)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        d_scr = torch.empty_like(d_tok)
+
+        def copies():
+            with torch.cuda.stream(s_in):
+                d_scr.copy_(h_tok_t, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out_t.copy_(d_out, non_blocking=True)
+
+        keep = h_out[idx].copy()
+        copies()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copies()
+        torch.cuda.synchronize()
+        floor_ms = (time.perf_counter() - t0) / 3 * 1e3
+        if world > 1:
+            tt = torch.tensor([floor_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            floor_ms = float(tt.item())
+        e2e["copy_floor_ms"] = floor_ms
+        e2e["frac_of_copy_floor"] = floor_ms / e2e["ms_per_step"]
+        del d_scr
+        assert np.array_equal(h_out[idx], keep)  # d_out holds the same signatures the host path produced
         slices = max(-(-n // (128 << 10)), -(-(n * t) // (16 << 20)))
         e2e_launches = slices * args.steps
 

@@ -820,7 +820,13 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
     const size_t tsz = token_is_u64 ? 8 : 4, osz = out_is_u64 ? 8 : 4;
     const int K = perm->num_perm;
     // slice limits: ~16 Mi tokens and 128 Ki documents per slice keep each copy in the MB range
-    const int64_t max_tok = 16ll << 20, max_docs = 128ll << 10;
+    // (DSK_SLICE_TOKENS overrides the token limit: a tuning knob for the copy/compute overlap, not a semantic one)
+    int64_t max_tok = 16ll << 20;
+    const int64_t max_docs = 128ll << 10;
+    if (const char *e = getenv("DSK_SLICE_TOKENS")) {
+        const long long v = atoll(e);
+        if (v >= 4096) max_tok = v;
+    }
 
     std::lock_guard<std::mutex> lk(g_pipe_mu);
     int prev = 0;
