@@ -45,7 +45,7 @@ SIGNATURES = {
     "dsk_sig_merge_min": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dsk_wmh_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "dsk_wmh_destroy": (None, [c_void_p]),
-    "dsk_wmh_minhash": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dsk_wmh_minhash": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "dsk_lsh_create": (c_int, [c_int, c_int, c_int, c_int64, c_int, ctypes.POINTER(c_void_p)]),
     "dsk_lsh_destroy": (None, [c_void_p]),
     "dsk_lsh_size": (c_int, [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),

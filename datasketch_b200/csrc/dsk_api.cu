@@ -484,8 +484,9 @@ void dsk_wmh_destroy(dsk_wmh *g) {
     delete g;
 }
 
-int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_out, int32_t *d_status, void *stream) {
-    if (!g || n < 0 || (n > 0 && (!d_v || !d_out || !d_status))) {
+int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_out, int32_t *d_status, int flags,
+                    void *stream) {
+    if (!g || n < 0 || (flags != DSK_WMH_MINHASH && flags != DSK_WMH_MINHASH_MANY) || (n > 0 && (!d_v || !d_out || !d_status))) {
         set_error("dsk_wmh_minhash: bad arguments");
         return DSK_ERR_INVALID;
     }
@@ -494,7 +495,7 @@ int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_ou
     if (rc) return rc;
     const size_t plane = (size_t)g->dim * g->ss_pad;
     DSK_CUDA(launch_wmh(g->d_par, g->d_par + plane, g->d_par + 2 * plane, g->ss, g->ss_pad, g->dim, d_v, n, d_out,
-                        d_status, dev->sm_count, (cudaStream_t)stream));
+                        d_status, flags == DSK_WMH_MINHASH_MANY, dev->sm_count, (cudaStream_t)stream));
     return DSK_OK;
 }
 

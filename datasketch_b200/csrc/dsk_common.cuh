@@ -59,7 +59,8 @@ cudaError_t launch_band_fingerprints(const uint32_t *sig, int64_t n, int k, int 
 
 cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, float *dst, cudaStream_t s);
 cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *betas_t, int ss, int ss_pad, int dim,
-                       const float *v, int64_t n, int64_t *out, int32_t *status, int sm_count, cudaStream_t s);
+                       const float *v, int64_t n, int64_t *out, int32_t *status, int many, int sm_count,
+                       cudaStream_t s);
 
 // ---- device-resident LSH index (lsh_kernels.cu) -------------------------------------------------
 struct LshDev {

@@ -7,6 +7,9 @@
 //   ln_y = (t - beta_i) * r_i
 //   ln_a = (ln_c_i - ln_y) - r_i
 //   k    = first index of the NaN-skipping minimum of ln_a;  out[i] = (k, int(t[k]))
+// MANY = true evaluates the reference's experimental minhash_many instead (weighted_minhash.py:221-224):
+//   ln_y = ((t - beta_i) + 1) * r_i;  ln_a = ln_c_i - ln_y      (same algebra, different float32 rounding)
+// and an all-zero row is reported in status[] (the caller returns None for it, :228 / :241-245).
 // Every float32 operation is a separate IEEE round-to-nearest op in exactly that order
 // (__fdiv_rn/__fadd_rn/__fsub_rn/__fmul_rn: no FMA contraction, no fast-math), so all steps after
 // the logarithm are bit-identical to numpy; the logarithm is log() in double rounded to float32
@@ -33,6 +36,19 @@ struct WmhParams {
     int32_t *status;                       // [n]: 1 = all-zero input (weighted_minhash.py:149-150)
 };
 
+// ln_a for one (sample, dim): each float32 operation rounded separately, in the reference's order
+template <bool MANY>
+__device__ __forceinline__ float wmh_ln_a(float t, float be, float r, float lc) {
+    if constexpr (MANY) {
+        const float ln_y = __fmul_rn(__fadd_rn(__fsub_rn(t, be), 1.0f), r);
+        return __fsub_rn(lc, ln_y);
+    } else {
+        const float ln_y = __fmul_rn(__fsub_rn(t, be), r);
+        return __fsub_rn(__fsub_rn(lc, ln_y), r);
+    }
+}
+
+template <bool MANY>
 __global__ void __launch_bounds__(kWmhThreads) wmh_kernel(const WmhParams p) {
     __shared__ __align__(16) float s_vlog[kTileD][kVec];  // [d][u]: 2 x LDS.128 per dim
     const int tid = threadIdx.x;
@@ -84,8 +100,7 @@ __global__ void __launch_bounds__(kWmhThreads) wmh_kernel(const WmhParams p) {
 #pragma unroll
                         for (int u = 0; u < kVec; ++u) {
                             const float t = floorf(__fadd_rn(__fdiv_rn(xs[u], r[q]), be[q]));
-                            const float ln_y = __fmul_rn(__fsub_rn(t, be[q]), r[q]);
-                            const float ln_a = __fsub_rn(__fsub_rn(lc[q], ln_y), r[q]);
+                            const float ln_a = wmh_ln_a<MANY>(t, be[q], r[q], lc[q]);
                             if (ln_a < best[u] || (bk[u] < 0 && ln_a == ln_a)) {  // NaN never wins; first index kept on ties
                                 best[u] = ln_a; bk[u] = d0 + dd + q; bt[u] = t;
                             }
@@ -102,8 +117,7 @@ __global__ void __launch_bounds__(kWmhThreads) wmh_kernel(const WmhParams p) {
 #pragma unroll
                     for (int u = 0; u < kVec; ++u) {
                         const float t = floorf(__fadd_rn(__fdiv_rn(xs[u], r), be));
-                        const float ln_y = __fmul_rn(__fsub_rn(t, be), r);
-                        const float ln_a = __fsub_rn(__fsub_rn(lc, ln_y), r);
+                        const float ln_a = wmh_ln_a<MANY>(t, be, r, lc);
                         if (ln_a < best[u] || (bk[u] < 0 && ln_a == ln_a)) {
                             best[u] = ln_a; bk[u] = d0 + dd; bt[u] = t;
                         }
@@ -140,7 +154,8 @@ cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, 
 }
 
 cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *betas_t, int ss, int ss_pad, int dim,
-                       const float *v, int64_t n, int64_t *out, int32_t *status, int sm_count, cudaStream_t s) {
+                       const float *v, int64_t n, int64_t *out, int32_t *status, int many, int sm_count,
+                       cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     WmhParams p;
     p.rs_t = rs_t; p.lncs_t = lncs_t; p.betas_t = betas_t;
@@ -151,7 +166,8 @@ cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *beta
     const int64_t cap = (int64_t)sm_count * 8;
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    wmh_kernel<<<grid, kWmhThreads, 0, s>>>(p);
+    if (many) wmh_kernel<true><<<grid, kWmhThreads, 0, s>>>(p);
+    else wmh_kernel<false><<<grid, kWmhThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 

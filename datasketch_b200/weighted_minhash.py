@@ -10,7 +10,7 @@ from __future__ import annotations
 import collections.abc
 import copy
 import ctypes
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
@@ -91,9 +91,8 @@ class WeightedMinHashGenerator:
         return st
 
     # -- sampling ----------------------------------------------------------------------------------
-    def minhash_batch(self, X, device: int = 0) -> np.ndarray:
-        """[n, dim] weights -> [n, sample_size, 2] int64 of (k, t) -- row i equals
-        ``self.minhash(X[i]).hashvalues``.  Raises ValueError if any row is all zeros."""
+    def _sample(self, X, device: int, many: bool):
+        """Device pass over [n, dim] weights -> ([n, sample_size, 2] int64 of (k, t), [n] bool all-zero rows)."""
         import torch
         if isinstance(X, np.ndarray):
             X = np.ascontiguousarray(X, dtype=np.float32)
@@ -111,11 +110,17 @@ class WeightedMinHashGenerator:
         d_out = torch.empty((n, self.sample_size, 2), dtype=torch.int64, device=d_v.device)
         d_st = torch.empty((n,), dtype=torch.int32, device=d_v.device)
         with torch.cuda.device(device):
-            nv.check(nv.load().dsk_wmh_minhash(h, d_v.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(),
+            nv.check(nv.load().dsk_wmh_minhash(h, d_v.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), int(many),
                                                torch.cuda.current_stream(d_v.device).cuda_stream))
-        if n and bool(d_st.any().item()):
+        return d_out.cpu().numpy(), d_st.cpu().numpy().astype(bool)
+
+    def minhash_batch(self, X, device: int = 0) -> np.ndarray:
+        """[n, dim] weights -> [n, sample_size, 2] int64 of (k, t) -- row i equals
+        ``self.minhash(X[i]).hashvalues``.  Raises ValueError if any row is all zeros."""
+        out, empty = self._sample(X, device, many=False)
+        if empty.any():
             raise ValueError("Input is all zeros")
-        return d_out.cpu().numpy()
+        return out
 
     def minhash(self, v) -> WeightedMinHash:
         """One weighted Jaccard vector -> WeightedMinHash (weighted_minhash.py:123-159; same checks)."""
@@ -129,16 +134,32 @@ class WeightedMinHashGenerator:
         out = self.minhash_batch(v.reshape(1, -1))
         return WeightedMinHash(self.seed, out[0].astype(int, copy=False))
 
-    def minhash_many(self, X) -> List[WeightedMinHash]:
-        """Batch convenience: one WeightedMinHash per row, each equal to ``minhash(row)``.
+    def minhash_many(self, X, device: int = 0) -> List[Optional[WeightedMinHash]]:
+        """A matrix of weighted Jaccard vectors (rows; numpy or scipy.sparse) -> one WeightedMinHash per
+        row, ``None`` for an all-zero row (weighted_minhash.py:161-247; same checks and return type).
 
-        Note: the reference's experimental ``minhash_many`` (weighted_minhash.py:161-247) uses a
-        different sampling formula and returns different values than ``minhash``; it is outside
-        this engine's scope.  Here every row follows ``minhash`` exactly."""
-        if hasattr(X, "toarray"):
-            X = X.toarray()
-        X = np.asarray(X)
-        if X.ndim == 1:
-            X = X.reshape(1, -1)
-        out = self.minhash_batch(X)
-        return [WeightedMinHash(self.seed, row.astype(int, copy=False)) for row in out]
+        The reference's experimental method rounds ``ln_a`` in a different order than ``minhash``
+        (:221-224: ``ln_y = (t - beta + 1) * r; ln_a = ln_c - ln_y``); the kernel's
+        ``DSK_WMH_MINHASH_MANY`` mode follows that order, so the values are the reference's
+        ``minhash_many`` values, not necessarily ``minhash``'s.  Rows go to the device densified, in
+        slabs of at most 256 MB."""
+        sparse = hasattr(X, "tocsr") and hasattr(X, "nnz")
+        if not sparse and not isinstance(X, np.ndarray):
+            raise TypeError("Input X must be a sparse matrix or numpy matrix")
+        if X.ndim != 2:
+            raise ValueError("Input must have two dimensions")
+        if X.shape[1] != self.dim:
+            raise ValueError("Input dimension mismatch, expecting %d" % self.dim)
+        if sparse:
+            X = X.tocsr()
+        n = X.shape[0]
+        ret: List[Optional[WeightedMinHash]] = [None] * n
+        slab = max(1, (256 << 20) // (4 * max(self.dim, 1)))
+        for r0 in range(0, n, slab):
+            part = X[r0:r0 + slab]
+            dense = np.asarray(part.toarray() if sparse else part, dtype=np.float32)
+            out, empty = self._sample(dense, device, many=True)
+            for i in range(out.shape[0]):
+                if not empty[i]:
+                    ret[r0 + i] = WeightedMinHash(self.seed, out[i].astype(int, copy=False))
+        return ret

@@ -148,13 +148,17 @@ DSK_API int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm
  * of WeightedMinHashGenerator.minhash (:147-158) for a batch of n vectors:
  *   d_v      [n, dim] float32 weights (zeros are skipped, :148-152)
  *   d_out    [n, sample_size, 2] int64: (k, int(t_k)) per sample (:158)
- *   d_status [n] int32: 1 where the input row is all zeros (reference: ValueError, :149-150) */
+ *   d_status [n] int32: 1 where the input row is all zeros (reference: ValueError, :149-150)
+ *   flags    DSK_WMH_MINHASH (0), or DSK_WMH_MINHASH_MANY: the float32 operation order of the
+ *            reference's experimental minhash_many (:221-224; an all-zero row is None there, :241-245) */
+#define DSK_WMH_MINHASH 0
+#define DSK_WMH_MINHASH_MANY 1
 typedef struct dsk_wmh dsk_wmh;
 DSK_API int dsk_wmh_create(const float *h_rs, const float *h_ln_cs, const float *h_betas, int sample_size, int dim,
                            int device, dsk_wmh **out);
 DSK_API void dsk_wmh_destroy(dsk_wmh *g);
 DSK_API int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_out, int32_t *d_status,
-                            void *stream);
+                            int flags, void *stream);
 
 /* ---- device-resident MinHashLSH index ------------------------------------------------------
  * Replaces the bucket step of MinHashLSH._insert / query over dict storage

@@ -166,6 +166,33 @@ def gen_wmh():
     np.savez_compressed(os.path.join(OUT, "wmh.npz"), **d)
 
 
+def gen_wmh_many():
+    """WeightedMinHashGenerator.minhash_many (weighted_minhash.py:161-247), dense and scipy.sparse input,
+    with all-zero rows (-> None)."""
+    import scipy.sparse
+    d = {}
+    for dim, ss, seed, nvec, tag in [(64, 16, 1, 40, "small"), (5, 8, 3, 9, "tiny"), (300, 32, 7, 25, "mid")]:
+        g = WeightedMinHashGenerator(dim, ss, seed)
+        rs = np.random.RandomState(14)
+        X = np.floor(rs.uniform(0, 6, (nvec, dim))).astype(np.float32)   # integer frequencies, many zeros
+        X[rs.uniform(size=X.shape) < 0.5] = 0
+        X[3] = 0
+        X[nvec - 1] = 0
+        X[5] = rs.uniform(0, 1e-3, dim)                                   # tiny weights: negative logs
+        dense = g.minhash_many(X)
+        sparse = g.minhash_many(scipy.sparse.csr_matrix(X))
+        null = np.array([m is None for m in dense])
+        assert (null == np.array([m is None for m in sparse])).all() and null[3] and null[nvec - 1]
+        out = np.zeros((nvec, ss, 2), dtype=np.int64)
+        for i, (a, b) in enumerate(zip(dense, sparse)):
+            if a is not None:
+                assert np.array_equal(a.hashvalues, b.hashvalues)
+                out[i] = a.hashvalues
+        d[f"{tag}_X"], d[f"{tag}_out"], d[f"{tag}_null"] = X, out, null
+        d[f"{tag}_cfg"] = np.array([dim, ss, seed], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "wmh_many.npz"), **d)
+
+
 def gen_lsh():
     d = {}
     rows = []
@@ -270,6 +297,7 @@ if __name__ == "__main__":
     gen_minhash()
     gen_lean()
     gen_wmh()
+    gen_wmh_many()
     gen_lsh()
     gen_bbit()
     gen_forest()

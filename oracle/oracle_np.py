@@ -215,6 +215,40 @@ def wmh_minhash(v, rs: np.ndarray, ln_cs: np.ndarray, betas: np.ndarray) -> np.n
     return out
 
 
+def wmh_minhash_many(X, rs: np.ndarray, ln_cs: np.ndarray, betas: np.ndarray) -> list:
+    """Per row of X: (sample_size, 2) int array of (k, t_k), or None for an all-zero row
+    (datasketch/weighted_minhash.py:161-247, the experimental batch method).
+
+    Same sampling as ``wmh_minhash`` but the float32 roundings differ (:221-224):
+    t = floor((log x / r) + beta); ln_y = ((t - beta) + 1) * r; ln_a = ln_c - ln_y; the argmin runs
+    over the row's non-zero columns in index order (first minimum wins, :234-235).
+    """
+    X = np.asarray(X.toarray() if hasattr(X, "toarray") else X)
+    if X.ndim != 2:
+        raise ValueError("Input must have two dimensions")
+    ss, dim = rs.shape
+    if X.shape[1] != dim:
+        raise ValueError("Input dimension mismatch, expecting %d" % dim)
+    X = X.astype(np.float32)
+    ret = []
+    for row in X:
+        cidx = np.nonzero(row)[0]
+        if cidx.size == 0:
+            ret.append(None)
+            continue
+        log_data = np.log(row[cidx])                    # float32
+        r, be, lc = rs[:, cidx], betas[:, cidx], ln_cs[:, cidx]
+        t = np.floor(log_data[None, :] / r + be)
+        ln_y = (t - be + 1) * r
+        ln_a = lc - ln_y
+        am = np.argmin(ln_a, axis=1)
+        out = np.zeros((ss, 2), dtype=int)
+        out[:, 0] = cidx[am]
+        out[:, 1] = t[np.arange(ss), am]
+        ret.append(out)
+    return ret
+
+
 def wmh_jaccard(hv1: np.ndarray, hv2: np.ndarray) -> float:
     """Fraction of samples with equal (k,t) rows (datasketch/weighted_minhash.py:55-60)."""
     inter = 0

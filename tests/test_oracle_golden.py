@@ -158,3 +158,20 @@ def test_lsh_params_keys_query(golden):
     for i, row in enumerate(g["abc_sig"]):
         l2.insert(i, row)
     assert sorted(l2.query(g["abc_sig"][0])) == g["abc_query0"].tolist() == [0, 1]
+
+
+def test_wmh_minhash_many(golden):
+    """The oracle's minhash_many restatement against the reference's own outputs (dense == sparse there)."""
+    g = golden("wmh_many")
+    for tag in ("small", "tiny", "mid"):
+        dim, ss, seed = (int(x) for x in g[f"{tag}_cfg"])
+        got = o.wmh_minhash_many(g[f"{tag}_X"], *o.wmh_params(dim, ss, seed))
+        null = g[f"{tag}_null"]
+        assert [m is None for m in got] == null.tolist() and null.any()
+        for i, m in enumerate(got):
+            if m is not None:
+                assert m.dtype == int and np.array_equal(m, g[f"{tag}_out"][i])
+    with pytest.raises(ValueError):
+        o.wmh_minhash_many(np.ones(5), *o.wmh_params(5, 4, 1))
+    with pytest.raises(ValueError):
+        o.wmh_minhash_many(np.ones((2, 3)), *o.wmh_params(5, 4, 1))

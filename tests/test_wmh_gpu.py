@@ -87,8 +87,16 @@ def test_wmh_api_contract(dsk):
         mg.minhash_batch(np.array([[1, 2, 3], [0, 0, 0]], dtype=np.float32))
     a, b = mg.minhash([1, 2, 3]), mg.minhash([1, 2, 3])
     assert a == b and a.jaccard(b) == 1.0 and 0.0 <= a.jaccard(mg.minhash([3, 2, 1])) <= 1.0
-    many = mg.minhash_many(np.array([[1, 2, 3], [3, 2, 1]]))
-    assert many[0] == a and len(many) == 2
+    many = mg.minhash_many(np.array([[1, 2, 3], [3, 2, 1], [0, 0, 0]]))
+    want_many = o.wmh_minhash_many(np.array([[1, 2, 3], [3, 2, 1], [0, 0, 0]]), *o.wmh_params(3, 4, 1))
+    assert len(many) == 3 and many[2] is None and want_many[2] is None
+    assert all(np.array_equal(many[i].hashvalues, want_many[i]) for i in range(2))
+    with pytest.raises(TypeError):
+        mg.minhash_many([[1, 2, 3]])               # reference: only numpy / scipy.sparse matrices
+    with pytest.raises(ValueError):
+        mg.minhash_many(np.array([1, 2, 3]))       # "Input must have two dimensions"
+    with pytest.raises(ValueError):
+        mg.minhash_many(np.ones((2, 4)))
     g2 = pickle.loads(pickle.dumps(mg))
     assert g2.minhash([1, 2, 3]) == a
 
@@ -107,3 +115,22 @@ def test_wmh_random_batch_vs_oracle(dsk):
         if (got[u] != want[u]).any():
             assert _explain_mismatch(V[u], *par, got[u], want[u]) == []
     assert int((got != want).any(axis=2).sum()) <= 2
+
+
+@pytest.mark.parametrize("tag", ["small", "tiny", "mid"])
+def test_wmh_minhash_many_matches_reference_fixture(dsk, golden, tag):
+    """minhash_many (dense and scipy.sparse input, all-zero rows -> None) against the outputs the
+    reference produced for the same matrices (weighted_minhash.py:161-247)."""
+    import scipy.sparse
+    g = golden("wmh_many")
+    dim, ss, seed = (int(x) for x in g[f"{tag}_cfg"])
+    X, want, null = g[f"{tag}_X"], g[f"{tag}_out"], g[f"{tag}_null"]
+    gen = dsk.WeightedMinHashGenerator(dim, ss, seed)
+    for inp in (X, scipy.sparse.csr_matrix(X), scipy.sparse.coo_matrix(X)):
+        got = gen.minhash_many(inp)
+        assert isinstance(got, list) and len(got) == len(X)
+        assert [m is None for m in got] == null.tolist()
+        for i, m in enumerate(got):
+            if m is not None:
+                assert isinstance(m, dsk.WeightedMinHash) and m.seed == seed and m.hashvalues.dtype == int
+                assert np.array_equal(m.hashvalues, want[i]), (tag, i)
