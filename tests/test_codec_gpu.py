@@ -180,3 +180,16 @@ def test_jaccard_topk_random_signatures_finds_planted_pairs(dsk):
     assert np.array_equal(idx[:64], wi)
     assert all(idx[i, 0] == i + 1 for i in range(0, 512, 2)) and all(idx[i, 0] == i - 1 for i in range(1, 512, 2))
     assert (jac[:, 0] >= 118 / 128).all() and (jac[:, 1] < 0.1).all()
+
+
+def test_sharded_topk_single_process_equals_kernel(dsk):
+    """world size 1: distributed.sharded_jaccard_topk is the plain kernel with self_base = 0."""
+    rs = np.random.RandomState(3)
+    sig = rs.randint(0, 4, size=(500, 64)).astype(np.uint32)
+    import torch
+    d = torch.from_numpy(sig.view(np.int32)).cuda()
+    cnt, idx = dsk.distributed.sharded_jaccard_topk(d, topk=7)
+    wc, wi = _topk_oracle(sig, sig, 7, 0)
+    assert np.array_equal(idx.cpu().numpy(), wi) and np.array_equal(cnt.cpu().numpy(), wc)
+    full, base, counts = dsk.distributed.gather_signature_blocks(d)
+    assert full is d and base == 0 and counts == [500]
