@@ -178,6 +178,13 @@ int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int 
         tab[3 * p->kpad + i] = (uint32_t)(h_b[i] >> 32);
         if (perm_unsafe_u32(h_a[i], h_b[i])) p->n_unsafe++;
     }
+    // Padding slots (a lane's permutations beyond num_perm; their results are never stored) repeat real
+    // permutations.  Zeros would make every token of a document tie in such a slot, and a tie sends the whole
+    // warp through the two-phase kernel's exact slow path for every document (measured: num_perm=192 ran 5x slower).
+    for (int i = num_perm; i < p->kpad; ++i) {
+        const int src = i % num_perm;
+        for (int q = 0; q < 4; ++q) tab[(size_t)q * p->kpad + i] = tab[(size_t)q * p->kpad + src];
+    }
     int prev = 0;
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
