@@ -4,7 +4,7 @@ A repeated token makes two 16-token blocks tie on the cheap phase-1 value L', wh
 permutation -- and with it the whole warp -- through the two-phase kernel's exact slow path for the
 document ("Known limitations").  This tool measures the penalty as a function of the share
 of a document's tokens that are repeats of earlier ones, and checks every configuration against the
-C oracle on a sample.  (Written at the end of round 1; not yet run on a GPU.)
+C oracle on a sample.  Round-1 result: profiles/r1z_repeated_tokens_penalty.jsonl.
 
     gpurun -- 'python tools/bench_duplicates.py > gpurun_out/dups.jsonl'
 """
