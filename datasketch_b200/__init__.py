@@ -16,11 +16,12 @@ from .b_bit_minhash import bBitMinHash  # noqa: E402
 from .weighted_minhash import WeightedMinHash, WeightedMinHashGenerator  # noqa: E402
 from .lsh import GpuLSH, MinHashLSH, MinHashLSHDeletionSession, MinHashLSHInsertionSession  # noqa: E402
 from .lshforest import GpuLSHForest, MinHashLSHForest  # noqa: E402
+from .lshensemble import MinHashLSHEnsemble  # noqa: E402
 from . import codec, distributed, engine  # noqa: E402
 
 # alias kept by the reference (datasketch/__init__.py:24-25)
 WeightedMinHashLSH = MinHashLSH
 
 __version__ = "0.1.0"
-__all__ = ["MinHash", "LeanMinHash", "bBitMinHash", "WeightedMinHash", "WeightedMinHashGenerator", "MinHashLSH", "GpuLSH", "MinHashLSHForest", "GpuLSHForest",
+__all__ = ["MinHash", "LeanMinHash", "bBitMinHash", "WeightedMinHash", "WeightedMinHashGenerator", "MinHashLSH", "GpuLSH", "MinHashLSHForest", "GpuLSHForest", "MinHashLSHEnsemble",
            "WeightedMinHashLSH", "MinHashLSHInsertionSession", "MinHashLSHDeletionSession", "sha1_hash32", "sha1_hash64", "engine", "codec", "distributed"]

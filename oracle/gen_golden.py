@@ -193,6 +193,57 @@ def gen_wmh_many():
     np.savez_compressed(os.path.join(OUT, "wmh_many.npz"), **d)
 
 
+def gen_ensemble():
+    """MinHashLSHEnsemble (lshensemble.py, lshensemble_partition.py): parameter tables, partition bounds and the
+    query results of a small indexed corpus."""
+    from datasketch.lshensemble import MinHashLSHEnsemble
+    from datasketch.lshensemble_partition import optimal_partitions
+    d = {}
+    rs = np.random.RandomState(31)
+    # partition bounds on a few size distributions (incl. num_part 1, 2, > domain)
+    cases = []
+    for n, num_part in [(1, 4), (5, 1), (6, 2), (9, 3), (12, 5), (20, 8), (30, 16), (7, 7), (7, 9)]:
+        sizes = np.sort(rs.choice(np.arange(1, 500), size=n, replace=False)).astype(np.int64)
+        counts = rs.randint(1, 30, size=n).astype(np.int64)
+        b = np.array(optimal_partitions(sizes, counts, num_part), dtype=np.int64)
+        cases.append((sizes, counts, num_part, b))
+    for i, (sizes, counts, num_part, b) in enumerate(cases):
+        d[f"part{i}_sizes"], d[f"part{i}_counts"], d[f"part{i}_bounds"] = sizes, counts, b
+        d[f"part{i}_num_part"] = np.array([num_part], dtype=np.int64)
+    d["n_part_cases"] = np.array([len(cases)], dtype=np.int64)
+    # parameter tables
+    for i, (thr, k, m, w) in enumerate([(0.5, 32, 4, (0.5, 0.5)), (0.8, 32, 8, (0.5, 0.5)), (0.2, 16, 4, (0.3, 0.7))]):
+        e = MinHashLSHEnsemble(threshold=thr, num_perm=k, num_part=2, m=m, weights=w)
+        d[f"par{i}_cfg"] = np.array([thr, k, m, w[0], w[1]], dtype=np.float64)
+        d[f"par{i}_params"], d[f"par{i}_xqs"] = e.params.astype(np.int64), e.xqs
+    # end to end: sets of very different sizes drawn from one vocabulary; queries are subsets of indexed sets
+    k = 32
+    vocab = rs.randint(0, 2 ** 32, size=3000, dtype=np.uint64)
+    sets = []
+    for i in range(160):
+        size = int(rs.choice([5, 8, 13, 20, 40, 80, 150, 300, 600]))
+        sets.append(rs.choice(vocab, size=size, replace=False))
+    for i in range(0, 160, 4):                      # containment pairs: sets[i] is a subset of sets[i+1]
+        big = sets[i + 1]
+        sets[i] = rs.choice(big, size=max(3, len(big) // 3), replace=False)
+    mhs = MinHash.bulk([[int(t) for t in s] for s in sets], num_perm=k, seed=1, hashfunc=ident)
+    sig = np.stack([m.hashvalues for m in mhs])
+    sizes = np.array([len(s) for s in sets], dtype=np.int64)
+    ens = MinHashLSHEnsemble(threshold=0.5, num_perm=k, num_part=6, m=4)
+    ens.index([(i, mhs[i], int(sizes[i])) for i in range(len(sets))])
+    d["e2e_sig"], d["e2e_sizes"] = sig.astype(np.uint32), sizes
+    d["e2e_cfg"] = np.array([0.5, k, 6, 4], dtype=np.float64)
+    d["e2e_lowers"] = np.array([-1 if x is None else x for x in ens.lowers], dtype=np.int64)
+    d["e2e_uppers"] = np.array([-1 if x is None else x for x in ens.uppers], dtype=np.int64)
+    qptr, qidx = [0], []
+    for i in range(len(sets)):
+        res = sorted(set(ens.query(mhs[i], int(sizes[i]))))
+        qidx.extend(res)
+        qptr.append(len(qidx))
+    d["e2e_qptr"], d["e2e_qidx"] = np.array(qptr, dtype=np.int64), np.array(qidx, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "ensemble.npz"), **d)
+
+
 def gen_lsh():
     d = {}
     rows = []
@@ -301,5 +352,6 @@ if __name__ == "__main__":
     gen_lsh()
     gen_bbit()
     gen_forest()
+    gen_ensemble()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
