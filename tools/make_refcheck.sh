@@ -7,15 +7,15 @@ set -e
 REF=${DATASKETCH_REF:-/root/reference}
 cd "$(dirname "$0")/.."
 rm -rf _refcheck && mkdir -p _refcheck/datasketch _refcheck/test
-for f in __init__.py utils.py test_minhash.py test_lean_minhash.py test_weighted_minhash.py test_lsh.py test_lshforest.py; do
+for f in __init__.py utils.py test_minhash.py test_lean_minhash.py test_weighted_minhash.py test_lsh.py test_lshforest.py test_lshensemble.py; do
   cp "$REF/test/$f" _refcheck/test/
 done
 cat > _refcheck/datasketch/__init__.py <<'PY'
 from datasketch_b200 import *  # noqa
-from datasketch_b200 import (MinHash, LeanMinHash, MinHashLSH, MinHashLSHForest, WeightedMinHash,
+from datasketch_b200 import (MinHash, LeanMinHash, MinHashLSH, MinHashLSHForest, MinHashLSHEnsemble, WeightedMinHash,
                              WeightedMinHashGenerator, bBitMinHash)
 PY
-for m in minhash lean_minhash weighted_minhash lsh lshforest b_bit_minhash hashfunc; do
+for m in minhash lean_minhash weighted_minhash lsh lshforest lshensemble b_bit_minhash hashfunc; do
 cat > _refcheck/datasketch/$m.py <<PY
 import datasketch_b200.$m as _m
 from datasketch_b200.$m import *  # noqa
