@@ -1,7 +1,11 @@
 // dsk_common.cuh -- shared device helpers (sm_100a): mbarrier / bulk-copy (TMA) PTX,
 // error plumbing.  No torch, no libraries: plain CUDA runtime + inline PTX.
 #pragma once
+#ifdef DSK_EMU  // CPU emulation of the kernel logic for the test-suite (tests/emu/cuda_emu.h); never defined in the product build
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -96,6 +100,7 @@ cudaError_t launch_forest_query(const uint32_t *sig, const int32_t *order, int64
                                 cudaStream_t s);
 
 // ---- PTX helpers -----------------------------------------------------------------
+#ifndef DSK_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -161,5 +166,6 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+#endif  // !DSK_EMU
 
 }  // namespace dsk

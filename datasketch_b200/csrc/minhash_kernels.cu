@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(256) seg_min_kernel(const uint32_t *__restrict
     }
 }
 
+#ifndef DSK_EMU
 cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
                            int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,
                            cudaStream_t s) {
@@ -551,7 +552,9 @@ cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_d
     seg_min_kernel<<<(unsigned)grid, 256, 0, s>>>(part, seg, n_docs, k, init, init_stride, init_is_u64, out, out_is_u64);
     return cudaGetLastError();
 }
+#endif  // !DSK_EMU
 
+#ifndef DSK_EMU  // the emulation harness (tests/emu) calls the kernel template directly
 // ---- launchers --------------------------------------------------------------------------------
 template <int P, int MODE, typename TokT, int OCC, int RESCAN = 0>
 static cudaError_t launch_bulk(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
@@ -634,5 +637,7 @@ cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n
     sig_merge_min_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, y, n, out);
     return cudaGetLastError();
 }
+
+#endif  // !DSK_EMU
 
 }  // namespace dsk

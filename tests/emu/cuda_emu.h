@@ -1,0 +1,115 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY.  A minimal SIMT shim that lets g++ compile the *unmodified* kernel
+// source of datasketch_b200/csrc/minhash_kernels.cu (with -DDSK_EMU) and run it on the CPU: every CUDA thread is
+// a host thread, a warp's collectives (__syncwarp, __shfl_sync, __all_sync, __any_sync) are pthread barriers over its
+// 32 lanes, __shared__ becomes static storage (CTAs run one after the other), and the mbarrier / bulk-copy PTX helpers
+// are replaced by a phase counter + memcpy.  It exists so that the kernel's control logic (ring protocol, block
+// patching, two-phase tracking, re-scan rules) is exercised against the oracle in the CPU test-suite, and so that
+// ThreadSanitizer can check the shared-memory ring for missing synchronisation.  It says nothing about performance.
+#pragma once
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+enum { cudaSuccess = 0 };
+
+struct uint3e { unsigned x, y, z; };
+struct uint4 { uint32_t x, y, z, w; };
+struct ulonglong2 { unsigned long long x, y; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+extern thread_local uint3e threadIdx;
+extern thread_local uint3e blockIdx;
+extern thread_local uint3e gridDim;
+extern thread_local uint3e blockDim;
+
+// ---- integer min / max as CUDA declares them ------------------------------------------------------------------
+#define DSK_EMU_MINMAX(T)                                      \
+    static inline T min(T a, T b) { return b < a ? b : a; }    \
+    static inline T max(T a, T b) { return a < b ? b : a; }
+DSK_EMU_MINMAX(int)
+DSK_EMU_MINMAX(unsigned)
+DSK_EMU_MINMAX(long)
+DSK_EMU_MINMAX(unsigned long)
+DSK_EMU_MINMAX(long long)
+DSK_EMU_MINMAX(unsigned long long)
+#undef DSK_EMU_MINMAX
+
+template <typename T>
+static inline T __ldg(const T *p) { return *p; }
+
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
+// ---- one warp = 32 host threads ----------------------------------------------------------------------------------
+struct EmuWarp {
+    pthread_barrier_t bar;
+    uint64_t slot[32];
+    std::atomic<unsigned> votes_all, votes_any;
+};
+extern thread_local EmuWarp *emu_warp;
+extern thread_local int emu_lane;
+
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { pthread_barrier_wait(&emu_warp->bar); }
+
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    emu_warp->slot[emu_lane] = raw;
+    pthread_barrier_wait(&emu_warp->bar);
+    raw = emu_warp->slot[src & 31];
+    pthread_barrier_wait(&emu_warp->bar);
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+
+static inline unsigned emu_ballot(bool pred) {
+    emu_warp->slot[emu_lane] = pred ? 1u : 0u;
+    pthread_barrier_wait(&emu_warp->bar);
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (unsigned)emu_warp->slot[i] << i;
+    pthread_barrier_wait(&emu_warp->bar);
+    return m;
+}
+static inline int __all_sync(unsigned, int pred) { return emu_ballot(pred != 0) == 0xFFFFFFFFu; }
+static inline int __any_sync(unsigned, int pred) { return emu_ballot(pred != 0) != 0u; }
+
+// ---- mbarrier + 1-D bulk copy: a phase counter and a memcpy ----------------------------------------------------------
+// The kernel's protocol per ring slot: lane 0 does arrive(.expect_tx) + bulk copy; everyone waits on the parity.
+// Here the copy is synchronous, so the phase completes when the copy (or the plain arrive) returns.
+namespace dsk {
+static inline std::atomic<uint64_t> *emu_bar(uint64_t *bar) { return reinterpret_cast<std::atomic<uint64_t> *>(bar); }
+static inline void mbar_init(uint64_t *bar, uint32_t) { emu_bar(bar)->store(0, std::memory_order_release); }
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_arrive_expect_tx(uint64_t *, uint32_t) {}
+static inline void mbar_arrive(uint64_t *bar) { emu_bar(bar)->fetch_add(1, std::memory_order_release); }
+static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    const bool done = (emu_bar(bar)->load(std::memory_order_acquire) & 1u) != parity;
+    if (!done) sched_yield();
+    return done;
+}
+static inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+static inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    memcpy(dst, src, bytes);
+    emu_bar(bar)->fetch_add(1, std::memory_order_release);
+}
+static inline uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+}  // namespace dsk

@@ -1,0 +1,59 @@
+// emu_tsan_main.cpp -- TEST INFRASTRUCTURE ONLY: the emulated kernel under ThreadSanitizer.
+//   g++ -std=c++17 -O1 -g -pthread -fsanitize=thread -DDSK_EMU -Itests/emu tests/emu/emu_minhash.cpp tests/emu/emu_tsan_main.cpp
+// Every CUDA thread is a host thread and the warp collectives are pthread barriers, so a shared-memory access that the
+// kernel does not order with __syncwarp / the mbarrier (e.g. refilling a ring slot that a lane is still reading) is a
+// data race TSan reports.  Also checks the results against a scalar evaluation of the reference formula.
+// Run with TSAN_OPTIONS=history_size=7: with the default history this TSan version cannot restore the earlier access's
+// stack for these short-lived lane threads and silently drops the report (seen in a control experiment).
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
+                                const uint64_t *a, const uint64_t *b, int k, int mode, int rescan, const void *init,
+                                int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int docs_per_unit,
+                                int grid_x);
+
+static uint64_t rng_state = 88172645463325252ull;
+static uint64_t rnd() {
+    rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
+    return rng_state;
+}
+
+int main() {
+    const uint64_t p61 = (1ull << 61) - 1;
+    const int k = 128, n_docs = 24;
+    std::vector<uint64_t> a(k), b(k);
+    for (int i = 0; i < k; ++i) { a[i] = 1 + rnd() % (p61 - 1); b[i] = rnd() % p61; }
+    std::vector<int64_t> off(n_docs + 1, 0);
+    for (int d = 0; d < n_docs; ++d) {
+        const int64_t len = (d % 6 == 0) ? 2500 + (int64_t)(rnd() % 1500) : (int64_t)(rnd() % 300);  // some longer than the ring
+        off[d + 1] = off[d] + (d == 3 ? 0 : len);
+    }
+    std::vector<uint32_t> tok(off[n_docs] + 16);
+    for (auto &t : tok) t = (uint32_t)rnd();
+    for (int d = 0; d < n_docs; ++d)          // repeated tokens: exact ties -> the re-scan paths run too
+        for (int64_t i = off[d] + 1; i < off[d + 1]; ++i)
+            if (rnd() % 5 == 0) tok[i] = tok[off[d] + (int64_t)(rnd() % (uint64_t)(i - off[d]))];
+    std::vector<uint32_t> want((size_t)n_docs * k, 0xFFFFFFFFu);
+    for (int d = 0; d < n_docs; ++d)
+        for (int64_t i = off[d]; i < off[d + 1]; ++i)
+            for (int j = 0; j < k; ++j) {
+                const uint64_t x = a[j] * (uint64_t)tok[i] + b[j];
+                const uint32_t r = (uint32_t)(x % p61);
+                if (r < want[(size_t)d * k + j]) want[(size_t)d * k + j] = r;
+            }
+    int bad = 0;
+    for (int mode = 0; mode < 3; ++mode)
+        for (int rescan = 0; rescan < (mode == 0 ? 2 : 1); ++rescan) {
+            std::vector<uint32_t> got((size_t)n_docs * k, 0);
+            emu_minhash_bulk(tok.data(), 0, off.data(), n_docs, a.data(), b.data(), k, mode, rescan, nullptr, 0, 0,
+                             got.data(), 0, 3, 2);
+            const bool ok = got == want;
+            printf("mode %d rescan %d: %s\n", mode, rescan, ok ? "identical" : "MISMATCH");
+            bad += !ok;
+        }
+    return bad ? 1 : 0;
+}

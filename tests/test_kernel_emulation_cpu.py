@@ -1,0 +1,164 @@
+"""The CUDA signature kernel's own source, run on the CPU against the oracle.
+
+``tests/emu/`` compiles ``datasketch_b200/csrc/minhash_kernels.cu`` with g++ (``-DDSK_EMU``): every CUDA thread is a
+host thread, warp collectives are barriers, the mbarrier / bulk-copy PTX is a phase counter + memcpy.  What this checks
+is the kernel's *logic* -- the per-warp ring protocol, block patching at document boundaries, the array's <16-byte
+tail, dynamic work units, the two-phase tracking with both re-scan variants, init merging, K slicing -- on the exact
+source that nvcc compiles for the B200 (the emulation hooks are preprocessor-only; the product build never defines
+DSK_EMU).  It says nothing about performance, and the GPU tests remain the parity gate for the compiled kernels.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_clib as oc
+from oracle import oracle_np as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+TWO_PHASE, DIRECT, EXACT = 0, 1, 2
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_minhash.so")
+    srcs = [os.path.join(EMU, "emu_minhash.cpp"), os.path.join(EMU, "cuda_emu.h"),
+            os.path.join(ROOT, "datasketch_b200", "csrc", "minhash_kernels.cu"),
+            os.path.join(ROOT, "datasketch_b200", "csrc", "dsk_common.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-DDSK_EMU", "-I" + EMU, "-shared", "-fPIC", "-o", so,
+                        srcs[0]], check=True)
+    lib = ctypes.CDLL(so)
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.emu_minhash_bulk.argtypes = [vp, ci, vp, i64, vp, vp, ci, ci, ci, vp, i64, ci, vp, ci, ci, ci]
+    lib.emu_minhash_bulk.restype = ci
+
+    def run(tok, off, perms, mode, rescan=0, init=None, out_u64=False, docs_per_unit=3, grid_x=1):
+        k, n = perms.shape[1], len(off) - 1
+        tok = np.ascontiguousarray(tok)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        out = np.zeros((n, k), dtype=np.uint64 if out_u64 else np.uint32)
+        a, b = np.ascontiguousarray(perms[0]), np.ascontiguousarray(perms[1])
+        ip, stride, i64f = None, 0, 0
+        if init is not None:
+            init = np.ascontiguousarray(init)
+            ip, stride, i64f = init.ctypes.data, (0 if init.ndim == 1 else k), int(init.dtype == np.uint64)
+        rc = lib.emu_minhash_bulk(tok.ctypes.data, int(tok.dtype == np.uint64), off.ctypes.data, n, a.ctypes.data,
+                                  b.ctypes.data, k, mode, rescan, ip, stride, i64f, out.ctypes.data, int(out_u64),
+                                  docs_per_unit, grid_x)
+        assert rc == 0
+        return out
+    return run
+
+
+def _ragged(rs, n, maxlen, extra_tail=0):
+    lens = rs.randint(0, maxlen + 1, size=n)
+    lens[:5] = [0, 1, 15, 16, 17]
+    lens[-1] = 0
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    off[-1] += extra_tail                      # makes the token count not a multiple of 4 (the <16-byte array tail)
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    return tok, off
+
+
+@pytest.mark.parametrize("k", [16, 64, 100, 128, 192, 256, 300])
+def test_all_modes_ragged_documents(emu, k):
+    rs = np.random.RandomState(k)
+    tok, off = _ragged(rs, 60, 150, extra_tail=3)
+    perms = o.init_permutations(k, 1)
+    want = oc.minhash_bulk_u32tok(tok, off, perms)
+    for mode in (TWO_PHASE, DIRECT, EXACT):
+        assert np.array_equal(emu(tok, off, perms, mode), want), (k, mode)
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=1), want)
+
+
+@pytest.mark.parametrize("rescan", [0, 1])
+@pytest.mark.parametrize("share", [0.05, 0.6])
+def test_repeated_tokens_take_the_rescan_and_stay_exact(emu, rescan, share):
+    rs = np.random.RandomState(int(share * 100) + rescan)
+    tok, off = _ragged(rs, 50, 400, extra_tail=1)
+    for d in range(len(off) - 1):
+        a, b = int(off[d]), int(off[d + 1])
+        if b - a > 1:
+            rep = np.nonzero(rs.uniform(size=b - a) < share)[0]
+            rep = rep[rep > 0]
+            tok[a + rep] = tok[a + (rs.uniform(size=len(rep)) * rep).astype(np.int64)]
+    for k in (128, 256):
+        perms = o.init_permutations(k, 2)
+        assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=rescan), oc.minhash_bulk_u32tok(tok, off, perms))
+
+
+@pytest.mark.parametrize("rescan", [0, 1])
+def test_structured_tokens_small_minimum_and_wrap(emu, rescan):
+    """Tiny and near-2^32 tokens: products next to the wrap, min L' < 7 cases, many exact ties."""
+    tok = np.concatenate([np.arange(0, 3000, dtype=np.uint32),
+                          (np.uint64(1 << 32) - np.arange(1, 3001, dtype=np.uint64)).astype(np.uint32),
+                          np.zeros(500, dtype=np.uint32), np.full(500, 0xFFFFFFFF, dtype=np.uint32)])
+    off = np.arange(0, len(tok) + 1, 125, dtype=np.int64)
+    perms = o.init_permutations(128, 3)
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=rescan), oc.minhash_bulk_u32tok(tok, off, perms))
+
+
+def test_long_documents_leave_the_ring_and_units_of_every_size(emu):
+    """Documents far longer than the 3 x 2 KB ring (winners evicted before phase 2), unit sizes 1 / 5 / 32, two CTAs."""
+    rs = np.random.RandomState(8)
+    lens = np.array([5000, 3, 2049, 0, 1537, 4096, 7, 2600], dtype=np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    perms = o.init_permutations(128, 1)
+    want = oc.minhash_bulk_u32tok(tok, off, perms)
+    for dpu, gx in ((1, 2), (5, 1), (32, 2)):
+        for rescan in (0, 1):
+            assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=rescan, docs_per_unit=dpu, grid_x=gx), want)
+    assert np.array_equal(emu(tok, off, perms, DIRECT, docs_per_unit=2, grid_x=2), want)
+
+
+def test_u64_tokens_init_merge_and_u64_output(emu):
+    rs = np.random.RandomState(4)
+    tok32, off = _ragged(rs, 30, 90)
+    k = 64
+    perms = o.init_permutations(k, 5)
+    tok64 = rs.randint(0, 1 << 63, size=len(tok32), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    want64 = oc.minhash_bulk_u64tok(tok64, off, perms)
+    assert np.array_equal(emu(tok64, off, perms, EXACT), want64)
+    base = oc.minhash_bulk_u32tok(tok32, off, perms)
+    row = rs.randint(0, 1 << 32, size=k, dtype=np.uint64)
+    mat = rs.randint(0, 1 << 32, size=base.shape, dtype=np.uint64)
+    got = emu(tok32, off, perms, TWO_PHASE, init=row, out_u64=True)
+    assert got.dtype == np.uint64 and np.array_equal(got, np.minimum(base.astype(np.uint64), row[None, :]))
+    got = emu(tok32, off, perms, DIRECT, init=mat.astype(np.uint32))
+    assert np.array_equal(got, np.minimum(base, mat.astype(np.uint32)))
+    got = emu(tok32, off, perms, EXACT, init=mat, out_u64=True)
+    assert np.array_equal(got, np.minimum(base.astype(np.uint64), mat))
+
+
+def test_thread_sanitizer_finds_no_race_in_the_ring_protocol():
+    """The emulated kernel under ThreadSanitizer (tests/emu/emu_tsan_main.cpp): a shared-memory access the kernel does not
+    order with __syncwarp / the mbarrier -- a ring slot refilled while a lane still reads it, the scratch line reused
+    too early -- shows up as a data race between the host threads that play the lanes.  (Control experiment, not
+    committed: deleting the __syncwarp after the scratch-line write makes TSan report the race and the results differ.)"""
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "emu_tsan")
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=thread", "-DDSK_EMU", "-I" + EMU,
+                            "-o", exe, os.path.join(EMU, "emu_minhash.cpp"), os.path.join(EMU, "emu_tsan_main.cpp")],
+                           capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + build.stderr[-200:])
+    env = dict(os.environ, TSAN_OPTIONS="history_size=7 halt_on_error=1 exitcode=66")   # history: see emu_tsan_main.cpp
+    run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=900)
+    text = run.stdout + run.stderr
+    if run.returncode not in (0, 1, 66) or "unexpected memory mapping" in text:
+        pytest.skip("ThreadSanitizer cannot run in this container: " + text[-200:])
+    assert "data race" not in text and run.returncode == 0, text[-2000:]
+    assert text.count("identical") == 4
