@@ -88,28 +88,75 @@ static inline unsigned emu_ballot(bool pred) {
 static inline int __all_sync(unsigned, int pred) { return emu_ballot(pred != 0) == 0xFFFFFFFFu; }
 static inline int __any_sync(unsigned, int pred) { return emu_ballot(pred != 0) != 0u; }
 
-// ---- mbarrier + 1-D bulk copy: a phase counter and a memcpy ----------------------------------------------------------
-// The kernel's protocol per ring slot: lane 0 does arrive(.expect_tx) + bulk copy; everyone waits on the parity.
-// Here the copy is synchronous, so the phase completes when the copy (or the plain arrive) returns.
+// ---- mbarrier + 1-D bulk copies, emulated ADVERSARIALLY --------------------------------------------------------------
+// On the GPU an async bulk copy lands at some point between its issue and the completion its waiter observes.  The
+// emulation takes both extremes at once: at issue time the destination is POISONED (a late reader of the old contents
+// sees garbage, and ThreadSanitizer sees the write), and the real data arrives only when the first waiter polls the
+// barrier (an early reader of the new contents sees poison).  Stores shared -> global are deferred likewise: the bytes
+// leave shared memory only when bulk_wait_read<N>() says the group has been read, so a buffer reused too early
+// corrupts the output.  mbarriers are a phase counter in the barrier's own 64-bit word.
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 namespace dsk {
+struct EmuPendingCopy { void *dst; const void *src; uint32_t bytes; };
+struct EmuAsync {
+    std::mutex mu;
+    std::unordered_map<uint64_t *, EmuPendingCopy> g2s;   // keyed by the mbarrier that will signal completion
+};
+inline EmuAsync &emu_async() { static EmuAsync a; return a; }
+
 static inline std::atomic<uint64_t> *emu_bar(uint64_t *bar) { return reinterpret_cast<std::atomic<uint64_t> *>(bar); }
-static inline void mbar_init(uint64_t *bar, uint32_t) { emu_bar(bar)->store(0, std::memory_order_release); }
+static inline void mbar_init(uint64_t *bar, uint32_t) {
+    std::lock_guard<std::mutex> lk(emu_async().mu);
+    emu_async().g2s.erase(bar);
+    emu_bar(bar)->store(0, std::memory_order_release);
+}
 static inline void fence_mbar_init() {}
 static inline void fence_proxy_async() {}
-static inline void mbar_arrive_expect_tx(uint64_t *, uint32_t) {}
+static inline void mbar_arrive_expect_tx(uint64_t *, uint32_t) {}   // the phase completes when the copy is delivered
 static inline void mbar_arrive(uint64_t *bar) { emu_bar(bar)->fetch_add(1, std::memory_order_release); }
 static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    const bool done = (emu_bar(bar)->load(std::memory_order_acquire) & 1u) != parity;
-    if (!done) sched_yield();
-    return done;
+    if ((emu_bar(bar)->load(std::memory_order_acquire) & 1u) != parity) return true;
+    {
+        std::lock_guard<std::mutex> lk(emu_async().mu);
+        auto it = emu_async().g2s.find(bar);
+        if (it != emu_async().g2s.end()) {            // deliver the copy now: the latest moment the hardware could
+            memcpy(it->second.dst, it->second.src, it->second.bytes);
+            emu_async().g2s.erase(it);
+            emu_bar(bar)->fetch_add(1, std::memory_order_release);
+            return true;
+        }
+    }
+    sched_yield();
+    return false;
 }
 static inline void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
 static inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    memcpy(dst, src, bytes);
-    emu_bar(bar)->fetch_add(1, std::memory_order_release);
+    memset(dst, 0xA5, bytes);                          // the earliest moment: the old contents are gone
+    std::lock_guard<std::mutex> lk(emu_async().mu);
+    emu_async().g2s[bar] = EmuPendingCopy{dst, src, bytes};
+}
+
+// shared -> global bulk stores: per issuing thread, grouped by bulk_commit(), drained by bulk_wait_read<N>()
+struct EmuStoreQueue { std::vector<std::vector<EmuPendingCopy>> groups; std::vector<EmuPendingCopy> open; };
+inline EmuStoreQueue &emu_stores() { static thread_local EmuStoreQueue q; return q; }
+static inline void bulk_s2g(void *dst, const void *src, uint32_t bytes) { emu_stores().open.push_back({dst, src, bytes}); }
+static inline void bulk_commit() {
+    emu_stores().groups.push_back(std::move(emu_stores().open));
+    emu_stores().open.clear();
+}
+template <int N>
+static inline void bulk_wait_read() {   // all but the newest N groups have been read out of shared memory
+    auto &g = emu_stores().groups;
+    while ((int)g.size() > N) {
+        for (const auto &c : g.front()) memcpy(c.dst, c.src, c.bytes);
+        g.erase(g.begin());
+    }
 }
 static inline uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 }  // namespace dsk
