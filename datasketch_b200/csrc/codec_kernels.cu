@@ -38,7 +38,7 @@ constexpr int kLeanStages = 4;  // tiles in flight per CTA (loads) -- Little's l
 
 template <bool PACK>
 __global__ void __launch_bounds__(kCodecThreads) lean_tile_kernel(const LeanParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    DSK_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t full[kLeanStages];
     const int K = p.k, RW = p.k + 3, R = p.rows_per_tile;
     const int in_rw = PACK ? K : RW, out_rw = PACK ? RW : K;
@@ -246,7 +246,7 @@ cudaError_t launch_bbit_pack(const uint32_t *sig, int64_t n, int k, int b, int s
     const int per = 64 / slot, nblk = (k + per - 1) / per;
     const uint32_t bmask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
     const int grid = (int)std::min<int64_t>((n * nblk + 255) / 256, (int64_t)sm_count * 16);
-    bbit_pack_kernel<<<grid, 256, 0, s>>>(sig, n, k, bmask, slot, nblk, out);
+    DSK_LAUNCH(bbit_pack_kernel, grid, 256, 0, s, sig, n, k, bmask, slot, nblk, out);
     return cudaGetLastError();
 }
 
@@ -255,7 +255,7 @@ cudaError_t launch_bbit_unpack(const uint64_t *blocks, int64_t n, int k, int slo
     if (n <= 0) return cudaSuccess;
     const int per = 64 / slot, nblk = (k + per - 1) / per;
     const int grid = (int)std::min<int64_t>((n * k + 255) / 256, (int64_t)sm_count * 16);
-    bbit_unpack_kernel<<<grid, 256, 0, s>>>(blocks, n, k, slot, nblk, sig);
+    DSK_LAUNCH(bbit_unpack_kernel, grid, 256, 0, s, blocks, n, k, slot, nblk, sig);
     return cudaGetLastError();
 }
 
@@ -293,11 +293,11 @@ cudaError_t launch_lean_pack(const void *sig, int sig_is_u64, int64_t n, int k, 
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (n + R - 1) / R;
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 3);
-        lean_tile_kernel<true><<<grid, kCodecThreads, smem, s>>>(p);
+        DSK_LAUNCH((lean_tile_kernel<true>), grid, kCodecThreads, smem, s, p);
     } else {
         const int64_t total = n * (k + 3);
         const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
-        lean_pack_simple_kernel<<<grid, 256, 0, s>>>(sig, sig_is_u64, n, k, w0, w1, w2, big_endian,
+        DSK_LAUNCH(lean_pack_simple_kernel, grid, 256, 0, s, sig, sig_is_u64, n, k, w0, w1, w2, big_endian,
                                                      reinterpret_cast<uint32_t *>(rec));
     }
     return cudaGetLastError();
@@ -320,11 +320,11 @@ cudaError_t launch_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t see
         if (e != cudaSuccess) return e;
         const int64_t ntiles = (n + R - 1) / R;
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count * 3);
-        lean_tile_kernel<false><<<grid, kCodecThreads, smem, s>>>(p);
+        DSK_LAUNCH((lean_tile_kernel<false>), grid, kCodecThreads, smem, s, p);
     } else {
         const int64_t total = n * (k + 3);
         const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
-        lean_unpack_simple_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t *>(rec), n, k, w0, w1, w2,
+        DSK_LAUNCH(lean_unpack_simple_kernel, grid, 256, 0, s, reinterpret_cast<const uint32_t *>(rec), n, k, w0, w1, w2,
                                                        big_endian, sig, sig_is_u64, d_status);
     }
     return cudaGetLastError();
@@ -334,7 +334,7 @@ cudaError_t launch_band_keys_be(const uint32_t *sig, int64_t n, int k, int b, in
                                 cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count * 8);
-    band_keys_be_kernel<<<grid, 256, 0, s>>>(sig, n, k, b * r, reinterpret_cast<uint2 *>(out));
+    DSK_LAUNCH(band_keys_be_kernel, grid, 256, 0, s, sig, n, k, b * r, reinterpret_cast<uint2 *>(out));
     return cudaGetLastError();
 }
 
@@ -343,7 +343,7 @@ cudaError_t launch_band_fingerprints(const uint32_t *sig, int64_t n, int k, int 
     if (n <= 0) return cudaSuccess;
     const int64_t total = n * b;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
-    band_fingerprint_kernel<<<grid, 256, 0, s>>>(sig, n, k, b, r, out);
+    DSK_LAUNCH(band_fingerprint_kernel, grid, 256, 0, s, sig, n, k, b, r, out);
     return cudaGetLastError();
 }
 

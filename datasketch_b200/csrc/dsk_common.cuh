@@ -12,6 +12,16 @@
 
 #include "../../include/dsk.h"
 
+// Kernel launch and dynamic shared memory go through two macros so that the CPU emulation used by the test-suite
+// (tests/emu, -DDSK_EMU) can run the launchers' host logic too.  In the product build they expand to the plain CUDA forms.
+#ifdef DSK_EMU
+#define DSK_LAUNCH(kernel, grid, block, smem, stream, ...) ::emu_launch(kernel, grid, block, smem, __VA_ARGS__)
+#define DSK_DYNAMIC_SMEM(name) unsigned char *name = ::emu_dynamic_smem()
+#else
+#define DSK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define DSK_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 namespace dsk {
 
 // ---- thread-local error string --------------------------------------------------

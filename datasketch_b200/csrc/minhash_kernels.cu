@@ -542,19 +542,16 @@ __global__ void __launch_bounds__(256) seg_min_kernel(const uint32_t *__restrict
     }
 }
 
-#ifndef DSK_EMU
 cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
                            int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,
                            cudaStream_t s) {
     if (n_docs <= 0) return cudaSuccess;
     int64_t grid = (n_docs * k + 255) / 256;
     if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
-    seg_min_kernel<<<(unsigned)grid, 256, 0, s>>>(part, seg, n_docs, k, init, init_stride, init_is_u64, out, out_is_u64);
+    DSK_LAUNCH(seg_min_kernel, (unsigned)grid, 256, 0, s, part, seg, n_docs, k, init, init_stride, init_is_u64, out, out_is_u64);
     return cudaGetLastError();
 }
-#endif  // !DSK_EMU
 
-#ifndef DSK_EMU  // the emulation harness (tests/emu) calls the kernel template directly
 // ---- launchers --------------------------------------------------------------------------------
 template <int P, int MODE, typename TokT, int OCC, int RESCAN = 0>
 static cudaError_t launch_bulk(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
@@ -571,7 +568,7 @@ static cudaError_t launch_bulk(const BulkParams &prm_in, int sm_count, cudaStrea
     cudaError_t e = cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned) * (size_t)slices, s);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    minhash_bulk_kernel<P, MODE, TokT, OCC, RESCAN><<<grid, kWarps * 32, 0, s>>>(prm);
+    DSK_LAUNCH((minhash_bulk_kernel<P, MODE, TokT, OCC, RESCAN>), grid, kWarps * 32, 0, s, prm);
     return cudaGetLastError();
 }
 
@@ -634,10 +631,9 @@ cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n
     if (n <= 0) return cudaSuccess;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
-    sig_merge_min_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, y, n, out);
+    DSK_LAUNCH(sig_merge_min_kernel, (unsigned)blocks, 256, 0, s, x, y, n, out);
     return cudaGetLastError();
 }
 
-#endif  // !DSK_EMU
 
 }  // namespace dsk

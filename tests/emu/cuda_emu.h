@@ -24,9 +24,20 @@
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+template <typename F>
+static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 struct uint3e { unsigned x, y, z; };
+struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
 struct ulonglong2 { unsigned long long x, y; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
@@ -52,6 +63,14 @@ static inline T __ldg(const T *p) { return *p; }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
+// __byte_perm(x, y, s): byte i of the result = byte (s >> 4i) & 7 of the 8-byte value {y, x}
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
+
 // ---- one warp = 32 host threads ----------------------------------------------------------------------------------
 struct EmuWarp {
     pthread_barrier_t bar;
@@ -60,6 +79,15 @@ struct EmuWarp {
 };
 extern thread_local EmuWarp *emu_warp;
 extern thread_local int emu_lane;
+
+// one CTA = its warps + a CTA-wide barrier + the dynamic shared memory of the launch
+struct EmuCta {
+    pthread_barrier_t bar;
+    unsigned char *dyn_smem;
+};
+extern thread_local EmuCta *emu_cta;
+static inline void __syncthreads() { pthread_barrier_wait(&emu_cta->bar); }
+static inline unsigned char *emu_dynamic_smem() { return emu_cta->dyn_smem; }
 
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { pthread_barrier_wait(&emu_warp->bar); }
 
@@ -87,6 +115,43 @@ static inline unsigned emu_ballot(bool pred) {
 }
 static inline int __all_sync(unsigned, int pred) { return emu_ballot(pred != 0) == 0xFFFFFFFFu; }
 static inline int __any_sync(unsigned, int pred) { return emu_ballot(pred != 0) != 0u; }
+
+// ---- launch: CTAs run one after the other (the kernels' __shared__ arrays are static), block_threads host threads each
+#include <thread>
+#include <tuple>
+#include <vector>
+template <typename... KArgs, typename... Args>
+static inline void emu_launch(void (*kernel)(KArgs...), dim3 grid, unsigned block_threads, size_t smem_bytes, Args... args) {
+    std::tuple<KArgs...> kargs(static_cast<KArgs>(args)...);
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            const unsigned nwarps = (block_threads + 31) / 32;
+            std::vector<EmuWarp> warps(nwarps);
+            for (unsigned w = 0; w < nwarps; ++w) {
+                const unsigned lanes = (w + 1) * 32 <= block_threads ? 32 : block_threads - w * 32;
+                pthread_barrier_init(&warps[w].bar, nullptr, lanes);
+            }
+            std::vector<unsigned char> dyn(smem_bytes + 256);
+            EmuCta cta;
+            pthread_barrier_init(&cta.bar, nullptr, block_threads);
+            cta.dyn_smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~(uintptr_t)127);
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < block_threads; ++t)
+                th.emplace_back([&, t] {
+                    threadIdx = {t, 0, 0};
+                    blockIdx = {bx, by, 0};
+                    gridDim = {grid.x, grid.y, 1};
+                    blockDim = {block_threads, 1, 1};
+                    emu_warp = &warps[t >> 5];
+                    emu_lane = (int)(t & 31);
+                    emu_cta = &cta;
+                    std::apply(kernel, kargs);
+                });
+            for (auto &x : th) x.join();
+            for (auto &w : warps) pthread_barrier_destroy(&w.bar);
+            pthread_barrier_destroy(&cta.bar);
+        }
+}
 
 // ---- mbarrier + 1-D bulk copies, emulated ADVERSARIALLY --------------------------------------------------------------
 // On the GPU an async bulk copy lands at some point between its issue and the completion its waiter observes.  The

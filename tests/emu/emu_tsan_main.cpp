@@ -11,6 +11,10 @@
 
 #include <vector>
 
+extern "C" int emu_lean_pack(const void *sig, int sig_is_u64, int64_t n, int k, int64_t seed, int big_endian, uint8_t *rec,
+                             int sm_count);
+extern "C" int emu_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t seed, int big_endian, void *sig, int sig_is_u64,
+                               int *status, int sm_count);
 extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
                                 const uint64_t *a, const uint64_t *b, int k, int mode, int rescan, const void *init,
                                 int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int docs_per_unit,
@@ -55,5 +59,19 @@ int main() {
             printf("mode %d rescan %d: %s\n", mode, rescan, ok ? "identical" : "MISMATCH");
             bad += !ok;
         }
+    {   // LeanMinHash codec: 4-stage bulk-copy tile pipeline, several tiles per CTA, ragged last tile
+        const int lk = 128;
+        const int64_t ln = 777;
+        std::vector<uint32_t> sig((size_t)ln * lk), back((size_t)ln * lk, 0);
+        for (auto &v : sig) v = (uint32_t)rnd();
+        std::vector<uint8_t> rec((size_t)ln * (12 + 4 * lk) + 64);
+        uint8_t *recp = rec.data() + (16 - (reinterpret_cast<uintptr_t>(rec.data()) & 15)) % 16;
+        int status = 0;
+        emu_lean_pack(sig.data(), 0, ln, lk, 42, 1, recp, 1);
+        emu_lean_unpack(recp, ln, lk, 42, 1, back.data(), 0, &status, 1);
+        const bool ok = back == sig && status == 0 && recp[0] == 0 && recp[7] == 42 && recp[11] == lk;
+        printf("lean codec round trip: %s\n", ok ? "identical" : "MISMATCH");
+        bad += !ok;
+    }
     return bad ? 1 : 0;
 }

@@ -1,11 +1,14 @@
 """The CUDA signature kernel's own source, run on the CPU against the oracle.
 
-``tests/emu/`` compiles ``datasketch_b200/csrc/minhash_kernels.cu`` with g++ (``-DDSK_EMU``): every CUDA thread is a
-host thread, warp collectives are barriers, the mbarrier / bulk-copy PTX is a phase counter + memcpy.  What this checks
-is the kernel's *logic* -- the per-warp ring protocol, block patching at document boundaries, the array's <16-byte
-tail, dynamic work units, the two-phase tracking with both re-scan variants, init merging, K slicing -- on the exact
-source that nvcc compiles for the B200 (the emulation hooks are preprocessor-only; the product build never defines
-DSK_EMU).  It says nothing about performance, and the GPU tests remain the parity gate for the compiled kernels.
+``tests/emu/`` compiles ``datasketch_b200/csrc/minhash_kernels.cu`` and ``codec_kernels.cu`` -- kernels AND launchers --
+with g++ (``-DDSK_EMU``): every CUDA thread is a host thread, warp / CTA barriers are pthread barriers, and the async
+bulk copies are emulated adversarially (destination poisoned at issue, data delivered only when a waiter polls the
+mbarrier, shared->global stores deferred until ``bulk_wait_read``).  What this checks is the *logic* -- the per-warp
+ring protocol, block patching at document boundaries, the array's <16-byte tail, dynamic work units, the two-phase
+tracking with both re-scan variants, init merging, K slicing, the launchers' choices, the 4-stage TMA tile pipeline of
+the LeanMinHash codec -- on the exact source that nvcc compiles for the B200 (the hooks are preprocessor-only; the
+product's SASS is byte-identical with and without them).  It says nothing about performance, and the GPU tests remain
+the parity gate for the compiled kernels.
 """
 import ctypes
 import os
@@ -29,9 +32,10 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 def emu():
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libemu_minhash.so")
-    srcs = [os.path.join(EMU, "emu_minhash.cpp"), os.path.join(EMU, "cuda_emu.h"),
+    so = os.path.join(out, "libemu_kernels.so")
+    srcs = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_emu.h"),
             os.path.join(ROOT, "datasketch_b200", "csrc", "minhash_kernels.cu"),
+            os.path.join(ROOT, "datasketch_b200", "csrc", "codec_kernels.cu"),
             os.path.join(ROOT, "datasketch_b200", "csrc", "dsk_common.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-DDSK_EMU", "-I" + EMU, "-shared", "-fPIC", "-o", so,
@@ -56,6 +60,7 @@ def emu():
                                   docs_per_unit, grid_x)
         assert rc == 0
         return out
+    run.lib = lib
     return run
 
 
@@ -151,7 +156,7 @@ def test_thread_sanitizer_finds_no_race_in_the_ring_protocol():
     os.makedirs(out, exist_ok=True)
     exe = os.path.join(out, "emu_tsan")
     build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=thread", "-DDSK_EMU", "-I" + EMU,
-                            "-o", exe, os.path.join(EMU, "emu_minhash.cpp"), os.path.join(EMU, "emu_tsan_main.cpp")],
+                            "-o", exe, os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "emu_tsan_main.cpp")],
                            capture_output=True, text=True)
     if build.returncode != 0:
         pytest.skip("ThreadSanitizer runtime not available: " + build.stderr[-200:])
@@ -161,4 +166,90 @@ def test_thread_sanitizer_finds_no_race_in_the_ring_protocol():
     if run.returncode not in (0, 1, 66) or "unexpected memory mapping" in text:
         pytest.skip("ThreadSanitizer cannot run in this container: " + text[-200:])
     assert "data race" not in text and run.returncode == 0, text[-2000:]
-    assert text.count("identical") == 4
+    assert text.count("identical") == 5
+
+
+# ---- codec kernels (codec_kernels.cu): TMA tile pipeline and the simple kernels ----------------------------------
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("k,n", [(128, 1000), (4, 333), (100, 75), (256, 41), (10, 50)])
+@pytest.mark.parametrize("bo", ["<", ">"])
+def test_lean_codec_tile_pipeline_and_fallbacks(emu, k, n, bo):
+    """k % 4 == 0 takes the 4-stage bulk-copy tile kernel (several tiles per CTA with sm_count = 1, ragged last tile),
+    other k the per-word kernels; both byte orders; u64 input; header validation on unpack."""
+    lib = emu.lib
+    rs = np.random.RandomState(k + n)
+    sig = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    seed = -123456789012345 if k % 8 else 7
+    big = int(bo == ">")
+    rec = np.zeros((n, 12 + 4 * k), dtype=np.uint8)
+    for sm_count in (1, 3):
+        rec[:] = 0
+        assert lib.emu_lean_pack(_ptr(sig), 0, n, k, ctypes.c_int64(seed), big, _ptr(rec), sm_count) == 0
+        for i in (0, n // 2, n - 1):
+            assert rec[i].tobytes() == o.lean_serialize(seed, sig[i].astype(np.uint64), bo)
+        back = np.zeros_like(sig)
+        status = np.zeros(1, dtype=np.int32)
+        assert lib.emu_lean_unpack(_ptr(rec), n, k, ctypes.c_int64(seed), big, _ptr(back), 0, _ptr(status), sm_count) == 0
+        assert status[0] == 0 and np.array_equal(back, sig)
+    rec64 = np.zeros_like(rec)
+    sig64 = sig.astype(np.uint64)
+    assert lib.emu_lean_pack(_ptr(sig64), 1, n, k, ctypes.c_int64(seed), big, _ptr(rec64), 2) == 0
+    assert np.array_equal(rec64, rec)
+    back64 = np.zeros((n, k), dtype=np.uint64)
+    status = np.zeros(1, dtype=np.int32)
+    assert lib.emu_lean_unpack(_ptr(rec), n, k, ctypes.c_int64(seed + 1), big, _ptr(back64), 1, _ptr(status), 2) == 0
+    assert status[0] == 1                                   # wrong seed in the header is flagged
+    if bo == "<":
+        assert np.array_equal(rec, oc.lean_pack_le(sig, seed))
+
+
+@pytest.mark.parametrize("k,b,r", [(128, 9, 13), (128, 32, 4), (256, 17, 15), (16, 4, 4), (32, 32, 1)])
+def test_band_keys_fingerprints_and_bbit_blocks(emu, golden, k, b, r):
+    lib = emu.lib
+    rs = np.random.RandomState(b * r)
+    n = 97
+    sig = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    sig[1] = sig[0]
+    keys = np.zeros((n, b, 8 * r), dtype=np.uint8)
+    assert lib.emu_band_keys(_ptr(sig), n, k, b, r, _ptr(keys)) == 0
+    assert np.array_equal(keys, oc.band_keys_be(sig, b, r))
+    fp = np.zeros((n, b), dtype=np.uint64)
+    assert lib.emu_band_fingerprints(_ptr(sig), n, k, b, r, _ptr(fp)) == 0
+    assert np.array_equal(fp[0], fp[1]) and len(np.unique(fp)) >= (n - 1) * b - 2
+    # b-bit blocks against the reference's pickle layout (tests/golden/bbit.npz pins the host class)
+    import struct
+    for bits, slot in ((1, 1), (2, 2), (3, 4), (8, 8), (13, 16), (32, 32)):
+        per = 64 // slot
+        nblk = -(-k // per)
+        blocks = np.zeros((n, nblk), dtype=np.uint64)
+        assert lib.emu_bbit_pack(_ptr(sig), n, k, bits, slot, _ptr(blocks)) == 0
+        masked = sig & np.uint32((1 << bits) - 1) if bits < 32 else sig
+        want0 = 0
+        for j, v in enumerate(masked[0][:per]):
+            want0 |= int(v) << (per - 1 - j) * slot
+        assert int(blocks[0, 0]) == want0
+        back = np.zeros_like(sig)
+        assert lib.emu_bbit_unpack(_ptr(blocks), n, k, slot, _ptr(back)) == 0
+        assert np.array_equal(back, masked)
+
+
+def test_seg_min_and_merge_kernels(emu):
+    lib = emu.lib
+    rs = np.random.RandomState(2)
+    k = 100
+    seg = np.array([0, 3, 3, 4, 10], dtype=np.int64)        # document 1 has no piece
+    part = rs.randint(0, 1 << 32, size=(10, k), dtype=np.uint64).astype(np.uint32)
+    init = rs.randint(0, 1 << 32, size=(4, k), dtype=np.uint64)
+    out = np.zeros((4, k), dtype=np.uint64)
+    assert lib.emu_seg_min(_ptr(part), _ptr(seg), 4, k, _ptr(init), k, 1, _ptr(out), 1) == 0
+    for d in range(4):
+        rows = part[seg[d]:seg[d + 1]].astype(np.uint64)
+        want = np.minimum(init[d], rows.min(axis=0)) if len(rows) else np.minimum(init[d], np.uint64(0xFFFFFFFF))
+        assert np.array_equal(out[d], want)
+    x = rs.randint(0, 1 << 32, size=5000, dtype=np.uint64).astype(np.uint32)
+    y = rs.randint(0, 1 << 32, size=5000, dtype=np.uint64).astype(np.uint32)
+    z = np.zeros_like(x)
+    assert lib.emu_sig_merge_min(_ptr(x), _ptr(y), 5000, _ptr(z)) == 0 and np.array_equal(z, np.minimum(x, y))
