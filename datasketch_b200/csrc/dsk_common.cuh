@@ -17,9 +17,11 @@
 #ifdef DSK_EMU
 #define DSK_LAUNCH(kernel, grid, block, smem, stream, ...) ::emu_launch(kernel, grid, block, smem, __VA_ARGS__)
 #define DSK_DYNAMIC_SMEM(name) unsigned char *name = ::emu_dynamic_smem()
+#define DSK_DYNAMIC_SMEM_T(type, name, align) type *name = reinterpret_cast<type *>(::emu_dynamic_smem())
 #else
 #define DSK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define DSK_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define DSK_DYNAMIC_SMEM_T(type, name, align) extern __shared__ __align__(align) type name[]
 #endif
 
 namespace dsk {

@@ -62,7 +62,7 @@ struct TopkParams {
 };
 
 __global__ void __launch_bounds__(kTopThreads) jaccard_topk_kernel(const TopkParams p) {
-    extern __shared__ __align__(16) uint32_t sm[];
+    DSK_DYNAMIC_SMEM_T(uint32_t, sm, 16);
     const int K = p.k;
     const int kpad = (K + kKc - 1) / kKc * kKc;
     uint32_t *sQ = sm;                              // [kpad][kTQ]
@@ -202,7 +202,7 @@ cudaError_t launch_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *d
     if (e != cudaSuccess) return e;
     int64_t grid = (nq + kTQ - 1) / kTQ;
     if (grid > (int64_t)sm_count * 3) grid = (int64_t)sm_count * 3;
-    jaccard_topk_kernel<<<(unsigned)grid, kTopThreads, smem, s>>>(p);
+    DSK_LAUNCH(jaccard_topk_kernel, (unsigned)grid, kTopThreads, smem, s, p);
     return cudaGetLastError();
 }
 
@@ -211,7 +211,7 @@ cudaError_t launch_jaccard_pairs(const uint32_t *sig, int64_t n_rows, int k, con
     if (m <= 0) return cudaSuccess;
     int64_t grid = (m + 7) / 8;
     if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
-    jaccard_pairs_kernel<<<(unsigned)grid, 256, 0, s>>>(sig, n_rows, k, ia, ib, m, out);
+    DSK_LAUNCH(jaccard_pairs_kernel, (unsigned)grid, 256, 0, s, sig, n_rows, k, ia, ib, m, out);
     return cudaGetLastError();
 }
 

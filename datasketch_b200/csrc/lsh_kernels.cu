@@ -170,7 +170,7 @@ cudaError_t launch_lsh_insert(const LshDev &ix, const uint32_t *new_sig, int64_t
     const int64_t total = n_new * ix.b;
     int64_t grid = (total + 255) / 256;
     if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
-    lsh_insert_kernel<<<(unsigned)grid, 256, 0, s>>>(ix, new_sig, doc0, n_new);
+    DSK_LAUNCH(lsh_insert_kernel, (unsigned)grid, 256, 0, s, ix, new_sig, doc0, n_new);
     return cudaGetLastError();
 }
 
@@ -179,8 +179,8 @@ cudaError_t launch_lsh_query(const LshDev &ix, const uint32_t *qsig, int64_t nq,
     if (nq <= 0) return cudaSuccess;
     int64_t grid = (nq + 7) / 8;
     if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
-    if (fill) lsh_query_kernel<true><<<(unsigned)grid, 256, 0, s>>>(ix, qsig, nq, n_docs, counts, ptr, out);
-    else lsh_query_kernel<false><<<(unsigned)grid, 256, 0, s>>>(ix, qsig, nq, n_docs, counts, ptr, out);
+    if (fill) DSK_LAUNCH((lsh_query_kernel<true>), (unsigned)grid, 256, 0, s, ix, qsig, nq, n_docs, counts, ptr, out);
+    else DSK_LAUNCH((lsh_query_kernel<false>), (unsigned)grid, 256, 0, s, ix, qsig, nq, n_docs, counts, ptr, out);
     return cudaGetLastError();
 }
 
@@ -188,9 +188,9 @@ cudaError_t launch_lsh_query(const LshDev &ix, const uint32_t *qsig, int64_t nq,
 cudaError_t launch_exclusive_scan(const int64_t *in, int64_t n, int64_t *out, int64_t *scratch, cudaStream_t s) {
     const int64_t nb = (n + kScanBlock - 1) / kScanBlock;
     if (n <= 0) return cudaMemsetAsync(out, 0, sizeof(int64_t), s);
-    scan_block_kernel<<<(unsigned)nb, kScanBlock, 0, s>>>(in, n, out, scratch);
-    scan_sums_kernel<<<1, 32, 0, s>>>(scratch, nb);
-    scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, s>>>(out, n, scratch, nb);
+    DSK_LAUNCH(scan_block_kernel, (unsigned)nb, kScanBlock, 0, s, in, n, out, scratch);
+    DSK_LAUNCH(scan_sums_kernel, 1, 32, 0, s, scratch, nb);
+    DSK_LAUNCH(scan_add_kernel, (unsigned)nb, kScanBlock, 0, s, out, n, scratch, nb);
     return cudaGetLastError();
 }
 
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) forest_query_kernel(const uint32_t *__res
                                                            const int32_t *__restrict__ order, int64_t n, int K, int l,
                                                            int k, const uint32_t *__restrict__ qsig, int64_t nq,
                                                            int topk, int32_t *__restrict__ out) {
-    extern __shared__ int32_t s_res[];  // [warps][topk]
+    DSK_DYNAMIC_SMEM_T(int32_t, s_res, 4);  // [warps][topk]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t *res = s_res + warp * topk;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -275,7 +275,7 @@ cudaError_t launch_forest_query(const uint32_t *sig, const int32_t *order, int64
     int64_t grid = (nq + 3) / 4;
     if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
     const size_t smem = (size_t)4 * topk * sizeof(int32_t);
-    forest_query_kernel<<<(unsigned)grid, 128, smem, s>>>(sig, order, n, K, l, k, qsig, nq, topk, out);
+    DSK_LAUNCH(forest_query_kernel, (unsigned)grid, 128, smem, s, sig, order, n, K, l, k, qsig, nq, topk, out);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,7 @@ cudaError_t launch_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t
     if (n_tok <= 0) return cudaSuccess;
     int64_t grid = (n_tok + 255) / 256;
     if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
-    sha1_tokens_kernel<<<(unsigned)grid, 256, 0, s>>>(bytes, off, n_tok, out, out_is_u64);
+    DSK_LAUNCH(sha1_tokens_kernel, (unsigned)grid, 256, 0, s, bytes, off, n_tok, out, out_is_u64);
     return cudaGetLastError();
 }
 

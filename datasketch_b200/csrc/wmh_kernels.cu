@@ -149,7 +149,7 @@ __global__ void wmh_transpose_kernel(const float *src, int ss, int dim, int ss_p
 }
 
 cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, float *dst, cudaStream_t s) {
-    wmh_transpose_kernel<<<256, 256, 0, s>>>(src, ss, dim, ss_pad, dst);
+    DSK_LAUNCH(wmh_transpose_kernel, 256, 256, 0, s, src, ss, dim, ss_pad, dst);
     return cudaGetLastError();
 }
 
@@ -166,8 +166,8 @@ cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *beta
     const int64_t cap = (int64_t)sm_count * 8;
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    if (many) wmh_kernel<true><<<grid, kWmhThreads, 0, s>>>(p);
-    else wmh_kernel<false><<<grid, kWmhThreads, 0, s>>>(p);
+    if (many) DSK_LAUNCH((wmh_kernel<true>), grid, kWmhThreads, 0, s, p);
+    else DSK_LAUNCH((wmh_kernel<false>), grid, kWmhThreads, 0, s, p);
     return cudaGetLastError();
 }
 
