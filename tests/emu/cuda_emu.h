@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <math.h>
+
 #include <atomic>
 
 #define __global__
@@ -33,6 +35,7 @@ static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess
 struct uint3e { unsigned x, y, z; };
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+struct float4 { float x, y, z, w; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 struct dim3 {
     unsigned x, y, z;
@@ -62,6 +65,35 @@ template <typename T>
 static inline T __ldg(const T *p) { return *p; }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
+// atomics: acquire-release so that ThreadSanitizer sees the lock / publish protocols the kernels build from them
+static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long val) {
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return cmp;
+}
+static inline int atomicCAS(int *p, int cmp, int val) {
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return cmp;
+}
+static inline int atomicExch(int *p, int val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+static inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) {
+    memcpy(dst, src, n);
+    return cudaSuccess;
+}
+
+// float32 operations rounded one by one (build the emulation with -ffp-contract=off so none are fused)
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, int n) {
+    n &= 31;
+    return n ? (hi << n) | (lo >> (32 - n)) : hi;
+}
 
 // __byte_perm(x, y, s): byte i of the result = byte (s >> 4i) & 7 of the 8-byte value {y, x}
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
@@ -103,6 +135,13 @@ static inline T __shfl_sync(unsigned, T v, int src) {
     T out;
     memcpy(&out, &raw, sizeof(T));
     return out;
+}
+
+template <typename T>
+static inline T __shfl_xor_sync(unsigned m, T v, int mask) { return __shfl_sync(m, v, emu_lane ^ mask); }
+template <typename T>
+static inline T __shfl_up_sync(unsigned m, T v, int delta) {
+    return __shfl_sync(m, v, emu_lane >= delta ? emu_lane - delta : emu_lane);
 }
 
 static inline unsigned emu_ballot(bool pred) {

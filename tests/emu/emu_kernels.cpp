@@ -1,5 +1,5 @@
-// emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY: runs the kernels AND launchers of datasketch_b200/csrc/minhash_kernels.cu
-// and codec_kernels.cu on host threads (tests/emu/cuda_emu.h) so the CPU test-suite can check their logic against the oracle.
+// emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY: runs the kernels AND launchers of datasketch_b200/csrc/*_kernels.cu
+// on host threads (tests/emu/cuda_emu.h) so the CPU test-suite can check their logic against the oracle.
 //   g++ -std=c++17 -O1 -pthread -DDSK_EMU -Itests/emu -shared -fPIC tests/emu/emu_kernels.cpp
 #include "cuda_emu.h"
 
@@ -10,6 +10,10 @@ thread_local EmuCta *emu_cta = nullptr;
 
 #include "../../datasketch_b200/csrc/minhash_kernels.cu"
 #include "../../datasketch_b200/csrc/codec_kernels.cu"
+#include "../../datasketch_b200/csrc/lsh_kernels.cu"
+#include "../../datasketch_b200/csrc/jaccard_kernels.cu"
+#include "../../datasketch_b200/csrc/sha1_kernels.cu"
+#include "../../datasketch_b200/csrc/wmh_kernels.cu"
 
 #include <vector>
 
@@ -72,4 +76,77 @@ extern "C" int emu_bbit_pack(const uint32_t *sig, int64_t n, int k, int b, int s
 }
 extern "C" int emu_bbit_unpack(const uint64_t *blocks, int64_t n, int k, int slot, uint32_t *sig) {
     return dsk::launch_bbit_unpack(blocks, n, k, slot, sig, 1, nullptr);
+}
+
+// ---- device-resident LSH index (lsh_kernels.cu), set up the way dsk_lsh_create does -----------------------------------
+struct EmuLsh {
+    dsk::LshDev dev;
+    std::vector<uint32_t> sig;
+    std::vector<uint64_t> slot_key;
+    std::vector<int32_t> slot_head, next;
+    int64_t n_docs = 0;
+};
+extern "C" void *emu_lsh_create(int k, int b, int r, int64_t cap_docs) {
+    EmuLsh *ix = new EmuLsh();
+    dsk::LshDev &v = ix->dev;
+    v.k = k; v.b = b; v.r = r; v.cap_docs = cap_docs;
+    v.cap_slots = 1024;
+    while (v.cap_slots < 2 * cap_docs) v.cap_slots <<= 1;
+    ix->sig.assign((size_t)cap_docs * k, 0u);
+    ix->slot_key.assign((size_t)b * v.cap_slots, ~0ull);          // cudaMemset 0xFF
+    ix->slot_head.assign((size_t)b * v.cap_slots, -1);
+    ix->next.assign((size_t)b * cap_docs, 0);
+    v.sig = ix->sig.data(); v.slot_key = ix->slot_key.data(); v.slot_head = ix->slot_head.data(); v.next = ix->next.data();
+    return ix;
+}
+extern "C" void emu_lsh_destroy(void *h) { delete static_cast<EmuLsh *>(h); }
+extern "C" int emu_lsh_insert(void *h, const uint32_t *sig, int64_t n, int sm_count) {
+    EmuLsh *ix = static_cast<EmuLsh *>(h);
+    if (ix->n_docs + n > ix->dev.cap_docs) return -1;
+    const int rc = dsk::launch_lsh_insert(ix->dev, sig, ix->n_docs, n, sm_count, nullptr);
+    ix->n_docs += n;
+    return rc;
+}
+// count -> exclusive scan -> fill, the sequence GpuLSH.query runs; ptr has nq + 1 entries, idx must hold ptr[nq]
+extern "C" int64_t emu_lsh_query_count(void *h, const uint32_t *q, int64_t nq, int64_t *ptr, int sm_count) {
+    EmuLsh *ix = static_cast<EmuLsh *>(h);
+    std::vector<int64_t> counts(nq + 1, 0), scratch(nq / 1024 + 2, 0);
+    if (dsk::launch_lsh_query(ix->dev, q, nq, ix->n_docs, counts.data(), nullptr, nullptr, 0, sm_count, nullptr)) return -1;
+    if (dsk::launch_exclusive_scan(counts.data(), nq, ptr, scratch.data(), nullptr)) return -1;
+    return ptr[nq];
+}
+extern "C" int emu_lsh_query_fill(void *h, const uint32_t *q, int64_t nq, const int64_t *ptr, int32_t *idx, int sm_count) {
+    EmuLsh *ix = static_cast<EmuLsh *>(h);
+    return dsk::launch_lsh_query(ix->dev, q, nq, ix->n_docs, nullptr, ptr, idx, 1, sm_count, nullptr);
+}
+extern "C" int emu_exclusive_scan(const int64_t *in, int64_t n, int64_t *out) {
+    std::vector<int64_t> scratch(n / 1024 + 2, 0);
+    return dsk::launch_exclusive_scan(in, n, out, scratch.data(), nullptr);
+}
+extern "C" int emu_forest_query(const uint32_t *sig, const int32_t *order, int64_t n, int K, int l, int k,
+                                const uint32_t *qsig, int64_t nq, int topk, int32_t *out, int sm_count) {
+    return dsk::launch_forest_query(sig, order, n, K, l, k, qsig, nq, topk, out, sm_count, nullptr);
+}
+extern "C" int emu_jaccard_pairs(const uint32_t *sig, int64_t n_rows, int k, const int64_t *ia, const int64_t *ib, int64_t m,
+                                 int32_t *out) {
+    return dsk::launch_jaccard_pairs(sig, n_rows, k, ia, ib, m, out, 1, nullptr);
+}
+extern "C" int emu_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *db, int64_t n, int k, int topk,
+                                int64_t self_base, int32_t *out_cnt, int64_t *out_idx, int sm_count) {
+    return dsk::launch_jaccard_topk(q, nq, db, n, k, topk, self_base, out_cnt, out_idx, sm_count, nullptr);
+}
+extern "C" int emu_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, void *out, int out_is_u64) {
+    return dsk::launch_sha1_tokens(bytes, off, n_tok, out, out_is_u64, 1, nullptr);
+}
+// rs / ln_cs / betas: [ss][dim] as the generator holds them; transposed to [dim][ss_pad] like dsk_wmh_create
+extern "C" int emu_wmh(const float *rs, const float *ln_cs, const float *betas, int ss, int dim, const float *v, int64_t n,
+                       int64_t *out, int32_t *status, int many) {
+    const int ss_pad = (ss + 31) / 32 * 32;
+    std::vector<float> par((size_t)3 * dim * ss_pad);
+    const float *src[3] = {rs, ln_cs, betas};
+    for (int i = 0; i < 3; ++i)
+        if (dsk::launch_wmh_transpose(src[i], ss, dim, ss_pad, par.data() + (size_t)i * dim * ss_pad, nullptr)) return -1;
+    const size_t plane = (size_t)dim * ss_pad;
+    return dsk::launch_wmh(par.data(), par.data() + plane, par.data() + 2 * plane, ss, ss_pad, dim, v, n, out, status, many,
+                           2, nullptr);
 }

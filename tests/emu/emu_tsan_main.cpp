@@ -15,6 +15,11 @@ extern "C" int emu_lean_pack(const void *sig, int sig_is_u64, int64_t n, int k, 
                              int sm_count);
 extern "C" int emu_lean_unpack(const uint8_t *rec, int64_t n, int k, int64_t seed, int big_endian, void *sig, int sig_is_u64,
                                int *status, int sm_count);
+extern "C" void *emu_lsh_create(int k, int b, int r, int64_t cap_docs);
+extern "C" void emu_lsh_destroy(void *h);
+extern "C" int emu_lsh_insert(void *h, const uint32_t *sig, int64_t n, int sm_count);
+extern "C" int64_t emu_lsh_query_count(void *h, const uint32_t *q, int64_t nq, int64_t *ptr, int sm_count);
+extern "C" int emu_lsh_query_fill(void *h, const uint32_t *q, int64_t nq, const int64_t *ptr, int32_t *idx, int sm_count);
 extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
                                 const uint64_t *a, const uint64_t *b, int k, int mode, int rescan, const void *init,
                                 int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int docs_per_unit,
@@ -71,6 +76,27 @@ int main() {
         emu_lean_unpack(recp, ln, lk, 42, 1, back.data(), 0, &status, 1);
         const bool ok = back == sig && status == 0 && recp[0] == 0 && recp[7] == 42 && recp[11] == lk;
         printf("lean codec round trip: %s\n", ok ? "identical" : "MISMATCH");
+        bad += !ok;
+    }
+    {   // LSH index: concurrent atomicCAS slot claims and atomicExch chain pushes from many threads, then queries
+        const int k = 32, b = 8, r = 4;
+        const int64_t n = 400;
+        std::vector<uint32_t> sig((size_t)n * k);
+        for (auto &v : sig) v = (uint32_t)(rnd() % 3);                     // low entropy: long chains, shared buckets
+        void *h = emu_lsh_create(k, b, r, n);
+        emu_lsh_insert(h, sig.data(), n, 2);
+        std::vector<int64_t> ptr(n + 1, 0);
+        const int64_t total = emu_lsh_query_count(h, sig.data(), n, ptr.data(), 2);
+        std::vector<int32_t> idx((size_t)(total > 0 ? total : 1), -1);
+        emu_lsh_query_fill(h, sig.data(), n, ptr.data(), idx.data(), 2);
+        bool ok = total >= n;
+        for (int64_t i = 0; i < n && ok; ++i) {                              // every document finds itself, exactly once
+            int self = 0;
+            for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p) self += idx[p] == (int32_t)i;
+            ok = self == 1;
+        }
+        emu_lsh_destroy(h);
+        printf("lsh insert/query: %s\n", ok ? "identical" : "MISMATCH");
         bad += !ok;
     }
     return bad ? 1 : 0;
