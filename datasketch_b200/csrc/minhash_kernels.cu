@@ -390,23 +390,31 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                     for (int j = 0; j < P; ++j) rs[j] = 0xFFFFFFFFu;
                     const int64_t b_first = start / kBlkTok, b_last = (end - 1) / kBlkTok;
                     const bool head_cut = (start % kBlkTok) != 0, tail_cut = (end % kBlkTok) != 0;
+                    auto partial = [&](int64_t blk) { return (blk == b_first && head_cut) || (blk == b_last && tail_cut); };
+                    // whole blocks are fetched one block ahead (four broadcast LDG.128, same address on every lane),
+                    // so the L2 latency of block i+1 overlaps the evaluation of block i
+                    uint4 nxt[4];
+                    auto fetch = [&](int64_t blk) {
+                        const uint4 *q = reinterpret_cast<const uint4 *>(tokens + blk * kBlkTok);   // 64-byte aligned
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) nxt[i] = __ldg(q + i);
+                    };
+                    if (!partial(b_first)) fetch(b_first);
                     for (int64_t blk = b_first; blk <= b_last; ++blk) {
                         uint32_t t[kBlkTok];
                         const int64_t base = blk * kBlkTok;
-                        if ((blk == b_first && head_cut) || (blk == b_last && tail_cut)) {
+                        if (partial(blk)) {
                             // boundary block: out-of-document slots duplicate an in-document token
 #pragma unroll
                             for (int i = 0; i < kBlkTok; ++i)
                                 t[i] = (uint32_t)__ldg(tokens + max(start, min(base + i, end - 1)));
                         } else {
-                            // whole block inside the document: 64-byte aligned, same address on every lane
-                            const uint4 *q = reinterpret_cast<const uint4 *>(tokens + base);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const uint4 v = __ldg(q + i);
-                                t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+                                t[4 * i] = nxt[i].x; t[4 * i + 1] = nxt[i].y; t[4 * i + 2] = nxt[i].z; t[4 * i + 3] = nxt[i].w;
                             }
                         }
+                        if (blk + 1 <= b_last && !partial(blk + 1)) fetch(blk + 1);
 #pragma unroll
                         for (int j = 0; j < P; ++j) {
                             if (!((need_slow >> j) & 1u)) continue;
