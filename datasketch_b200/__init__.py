@@ -9,7 +9,7 @@ from . import _native
 
 _native.load()  # fail loudly if the CUDA library is absent
 
-from .hashfunc import sha1_hash32, sha1_hash64  # noqa: E402
+from .hashfunc import murmur3_hash32, sha1_hash32, sha1_hash64, xxh32_hash32  # noqa: E402
 from .minhash import MinHash  # noqa: E402
 from .lean_minhash import LeanMinHash  # noqa: E402
 from .b_bit_minhash import bBitMinHash  # noqa: E402
@@ -24,4 +24,4 @@ WeightedMinHashLSH = MinHashLSH
 
 __version__ = "0.1.0"
 __all__ = ["MinHash", "LeanMinHash", "bBitMinHash", "WeightedMinHash", "WeightedMinHashGenerator", "MinHashLSH", "GpuLSH", "MinHashLSHForest", "GpuLSHForest", "MinHashLSHEnsemble",
-           "WeightedMinHashLSH", "MinHashLSHInsertionSession", "MinHashLSHDeletionSession", "sha1_hash32", "sha1_hash64", "engine", "codec", "distributed"]
+           "WeightedMinHashLSH", "MinHashLSHInsertionSession", "MinHashLSHDeletionSession", "sha1_hash32", "sha1_hash64", "xxh32_hash32", "murmur3_hash32", "engine", "codec", "distributed"]

@@ -670,6 +670,20 @@ int dsk_sha1_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64
     return DSK_OK;
 }
 
+int dsk_hash_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64_t n_tokens, int kind, uint32_t seed,
+                    uint32_t *d_out, void *stream) {
+    if (n_tokens < 0 || (kind != DSK_HASH_XXH32 && kind != DSK_HASH_MURMUR3_32) ||
+        (n_tokens > 0 && (!d_byte_offsets || !d_out))) {
+        set_error("dsk_hash_tokens: bad arguments (kind must be DSK_HASH_XXH32 or DSK_HASH_MURMUR3_32)");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    int rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_hash_tokens(d_bytes, d_byte_offsets, n_tokens, kind, seed, d_out, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 static int bbit_slot(int b) {
     if (b < 0 || b > 32) return -1;
     if (b == 1) return 1;

@@ -101,6 +101,8 @@ cudaError_t launch_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *d
 
 cudaError_t launch_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, void *out, int out_is_u64,
                                int sm_count, cudaStream_t s);
+cudaError_t launch_hash_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, int kind, uint32_t seed,
+                               uint32_t *out, int sm_count, cudaStream_t s);
 
 cudaError_t launch_bbit_pack(const uint32_t *sig, int64_t n, int k, int b, int slot, uint64_t *out, int sm_count,
                              cudaStream_t s);

@@ -163,10 +163,33 @@ def sha1_hash_tokens_device(flat_tokens, device: int = 0, out_u64: bool = False)
     return _sha1_blob_device(blob, boff, n, device, out_u64)
 
 
+def hash_tokens_device(flat_tokens, kind: int, seed: int = 0, device: int = 0):
+    """Device-side XXH32 (``kind`` 1) / MurmurHash3 x86_32 (``kind`` 2) of a flat list of byte strings -> CUDA int32
+    tensor holding the unsigned 32-bit hashes (``hashfunc.xxh32_hash32`` / ``murmur3_hash32`` per token)."""
+    import torch
+    nv.require_device(device)
+    n = len(flat_tokens)
+    lens = np.fromiter(map(len, flat_tokens), dtype=np.int64, count=n)
+    blob = bytearray().join(flat_tokens)
+    boff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=boff[1:])
+    if int(boff[-1]) != len(blob):
+        raise TypeError("tokens must be byte strings (item size 1)")
+    dev = torch.device("cuda", device)
+    d_bytes = (torch.frombuffer(blob, dtype=torch.uint8) if len(blob) else torch.zeros(1, dtype=torch.uint8)).to(dev)
+    d_boff = torch.from_numpy(boff).to(dev)
+    out = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    with torch.cuda.device(device):
+        nv.check(nv.load().dsk_hash_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n, int(kind), int(seed) & 0xFFFFFFFF,
+                                            out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return out[:n]
+
+
 def bulk_signatures_sha1(docs: Sequence[Sequence[bytes]], permutations: np.ndarray, init: Optional[np.ndarray] = None,
-                         device: int = 0) -> np.ndarray:
-    """``MinHash.bulk`` for byte tokens under the DEFAULT hash function, entirely on device:
-    SHA1-32 of every token (``dsk_sha1_tokens``) feeds the signature kernel without the hashes ever
+                         device: int = 0, hash_kind: int = 0) -> np.ndarray:
+    """``MinHash.bulk`` for byte tokens under a hash function the library has on device: the token hash
+    (``hash_kind`` 0 = SHA1-32 via ``dsk_sha1_tokens``, the reference's default; ``DSK_HASH_XXH32`` = 1 /
+    ``DSK_HASH_MURMUR3_32`` = 2 via ``dsk_hash_tokens``) feeds the signature kernel without the hashes ever
     visiting the host.  Returns the [N, K] uint64 matrix (the reference's dtype).
 
     Host packing is one C-level pass per document (``bytes.join`` while the document's tokens are
@@ -209,8 +232,12 @@ def bulk_signatures_sha1(docs: Sequence[Sequence[bytes]], permutations: np.ndarr
     d_boff.copy_(_pinned_stage("boff", 0).view(torch.int64)[:n_tok + 1], non_blocking=True)
     d_hash = torch.empty((max(n_tok, 4),), dtype=torch.int32, device=dev)
     with torch.cuda.device(device):
-        nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, d_hash.data_ptr(), 0,
-                                            torch.cuda.current_stream(dev).cuda_stream))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if hash_kind == 0:
+            nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, d_hash.data_ptr(), 0, st))
+        else:
+            nv.check(nv.load().dsk_hash_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, int(hash_kind), 0,
+                                                d_hash.data_ptr(), st))
     d_off = torch.from_numpy(off).to(dev)
     d_out = torch.empty((n, permutations.shape[1]), dtype=torch.int64, device=dev)
     d_init, stride = None, 0

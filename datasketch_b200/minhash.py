@@ -24,7 +24,7 @@ from typing import Callable, Generator, Iterable, List, Optional
 import numpy as np
 
 from . import engine
-from .hashfunc import sha1_hash32
+from .hashfunc import DEVICE_HASHES, sha1_hash32
 
 # minhash.py:27, :30-32
 hashvalue_byte_size = len(bytes(np.int64(42).data))
@@ -214,16 +214,19 @@ class MinHash:
         hf = proto.hashfunc
         batch: list = []
 
-        # With the reference's default hash function on byte tokens, hashing moves to the device too
-        # (dsk_sha1_tokens): same values as hashfunc.sha1_hash32, no per-token Python hashlib call.
-        device_sha1 = hf is sha1_hash32
+        # With a hash function the library has on device (the reference's default sha1_hash32, or the xxh32 /
+        # murmur3 functions of .hashfunc) hashing moves to the device too: same values, no per-token Python call.
+        try:
+            device_hash = DEVICE_HASHES.get(hf)
+        except TypeError:  # an unhashable callable
+            device_hash = None
 
         def run(docs):
             init = proto.hashvalues if not proto.is_empty() else None
             sig = None
-            if device_sha1:
+            if device_hash is not None:
                 try:
-                    sig = engine.bulk_signatures_sha1(docs, perms, init=init)
+                    sig = engine.bulk_signatures_sha1(docs, perms, init=init, hash_kind=device_hash[1])
                 except TypeError:
                     sig = None  # a non-bytes token: the per-token route below raises what the reference raises
             if sig is None:

@@ -221,6 +221,17 @@ DSK_API int dsk_bbit_unpack(const uint64_t *d_blocks, int64_t n, int num_perm, i
 DSK_API int dsk_sha1_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64_t n_tokens, void *d_out,
                             int out_is_u64, void *stream);
 
+/* ---- fast non-cryptographic token hashes on device ("next" row) -------------
+ * The hash functions the reference documents as `hashfunc` alternatives (docs/minhash.rst:79-112):
+ *   DSK_HASH_XXH32       XXH32(data, seed)             == xxhash.xxh32_intdigest(data, seed)
+ *   DSK_HASH_MURMUR3_32  MurmurHash3_x86_32(data, seed) == mmh3.hash(data, seed, signed=False)
+ * d_out[t] = 32-bit hash of d_bytes[d_byte_offsets[t] : d_byte_offsets[t+1]]; replaces the per-token
+ * Python call of minhash.py:263 when the user's hashfunc is one of these. */
+#define DSK_HASH_XXH32 1
+#define DSK_HASH_MURMUR3_32 2
+DSK_API int dsk_hash_tokens(const uint8_t *d_bytes, const int64_t *d_byte_offsets, int64_t n_tokens, int kind,
+                            uint32_t seed, uint32_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,6 +244,22 @@ def gen_ensemble():
     np.savez_compressed(os.path.join(OUT, "ensemble.npz"), **d)
 
 
+def gen_hashes():
+    """Token-hash fixtures from the third-party packages the reference's docs name (docs/minhash.rst:79-112).
+    Only `xxhash` is installed in the build container; MurmurHash3 is pinned by published vectors in the tests."""
+    import xxhash
+    rs = np.random.RandomState(77)
+    toks = [b"", b"a", b"abc", b"Hello", b"x" * 15, b"y" * 16, b"z" * 17, b"w" * 31, b"v" * 32, b"u" * 33] + \
+           [bytes(rs.randint(0, 256, size=rs.randint(0, 120)).astype(np.uint8)) for _ in range(400)]
+    blob = np.frombuffer(b"".join(toks), dtype=np.uint8)
+    off = np.zeros(len(toks) + 1, dtype=np.int64)
+    np.cumsum([len(t) for t in toks], out=off[1:])
+    d = {"blob": blob, "off": off, "xxhash_version": np.array([xxhash.VERSION])}
+    for seed in (0, 1, 0x9747B28C):
+        d[f"xxh32_seed{seed}"] = np.array([xxhash.xxh32_intdigest(t, seed) for t in toks], dtype=np.uint32)
+    np.savez_compressed(os.path.join(OUT, "hashes.npz"), **d)
+
+
 def gen_lsh():
     d = {}
     rows = []
@@ -353,5 +369,6 @@ if __name__ == "__main__":
     gen_bbit()
     gen_forest()
     gen_ensemble()
+    gen_hashes()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

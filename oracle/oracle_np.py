@@ -358,3 +358,68 @@ def permute_scalar(a: int, b: int, h: int) -> int:
     ((a*h + b) mod 2^64) mod (2^61-1), low 32 bits (minhash.py:223 / :295-296)."""
     x = (a * h + b) & ((1 << 64) - 1)
     return (x % ((1 << 61) - 1)) & 0xFFFFFFFF
+
+
+# ----------------------------------------------------------------------------
+# Non-cryptographic token hashes the reference documents as `hashfunc` choices
+# (docs/minhash.rst:79-112).  Third-party algorithms, absent from the reference's
+# tree: xxHash 32-bit (package `xxhash`, pinned by tests/golden/hashes.npz which
+# that package produced) and MurmurHash3 x86_32 (package `mmh3`, not installed
+# here: pinned by its published verification vectors in tests/test_oracle_golden.py).
+# Restated with numpy uint32 scalars (wrap-around arithmetic).
+# ----------------------------------------------------------------------------
+def _u32(x):
+    return np.uint32(int(x) & 0xFFFFFFFF)
+
+
+def _rol(x, n):
+    x = int(x)
+    return _u32((x << n) | (x >> (32 - n)))
+
+
+def xxh32(data: bytes, seed: int = 0) -> int:
+    d = np.frombuffer(bytes(data), dtype=np.uint8)
+    n = len(d)
+    P1, P2, P3, P4, P5 = (_u32(v) for v in (2654435761, 2246822519, 3266489917, 668265263, 374761393))
+    words = d[: n // 4 * 4].view("<u4") if n >= 4 else np.zeros(0, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        s32 = _u32(seed)
+        w = 0
+        if n >= 16:
+            acc = [s32 + P1 + P2, s32 + P2, s32, s32 - P1]
+            for stripe in range(n // 16):
+                for lane in range(4):
+                    acc[lane] = _rol(acc[lane] + words[4 * stripe + lane] * P2, 13) * P1
+            w = 4 * (n // 16)
+            h = _rol(acc[0], 1) + _rol(acc[1], 7) + _rol(acc[2], 12) + _rol(acc[3], 18)
+        else:
+            h = s32 + P5
+        h = h + _u32(n)
+        for q in range(w, n // 4):
+            h = _rol(h + words[q] * P3, 17) * P4
+        for byte in d[n // 4 * 4:]:
+            h = _rol(h + _u32(byte) * P5, 11) * P1
+        h = (h ^ (h >> np.uint32(15))) * P2
+        h = (h ^ (h >> np.uint32(13))) * P3
+        h = h ^ (h >> np.uint32(16))
+    return int(h)
+
+
+def murmur3_32(data: bytes, seed: int = 0) -> int:
+    d = np.frombuffer(bytes(data), dtype=np.uint8)
+    n = len(d)
+    C1, C2 = _u32(0xCC9E2D51), _u32(0x1B873593)
+    with np.errstate(over="ignore"):
+        h = _u32(seed)
+        for k in (d[: n // 4 * 4].view("<u4") if n >= 4 else []):
+            k = _rol(k * C1, 15) * C2
+            h = _rol(h ^ k, 13) * np.uint32(5) + _u32(0xE6546B64)
+        tail = d[n // 4 * 4:]
+        if len(tail):
+            k = _u32(sum(int(b) << (8 * i) for i, b in enumerate(tail)))
+            h = h ^ (_rol(k * C1, 15) * C2)
+        h = h ^ _u32(n)
+        h = (h ^ (h >> np.uint32(16))) * _u32(0x85EBCA6B)
+        h = (h ^ (h >> np.uint32(13))) * _u32(0xC2B2AE35)
+        h = h ^ (h >> np.uint32(16))
+    return int(h)

@@ -13,6 +13,7 @@ thread_local EmuCta *emu_cta = nullptr;
 #include "../../datasketch_b200/csrc/lsh_kernels.cu"
 #include "../../datasketch_b200/csrc/jaccard_kernels.cu"
 #include "../../datasketch_b200/csrc/sha1_kernels.cu"
+#include "../../datasketch_b200/csrc/hash_kernels.cu"
 #include "../../datasketch_b200/csrc/wmh_kernels.cu"
 
 #include <vector>
@@ -137,6 +138,9 @@ extern "C" int emu_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *d
 }
 extern "C" int emu_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, void *out, int out_is_u64) {
     return dsk::launch_sha1_tokens(bytes, off, n_tok, out, out_is_u64, 1, nullptr);
+}
+extern "C" int emu_hash_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, int kind, uint32_t seed, uint32_t *out) {
+    return dsk::launch_hash_tokens(bytes, off, n_tok, kind, seed, out, 1, nullptr);
 }
 // rs / ln_cs / betas: [ss][dim] as the generator holds them; transposed to [dim][ss_pad] like dsk_wmh_create
 extern "C" int emu_wmh(const float *rs, const float *ln_cs, const float *betas, int ss, int dim, const float *v, int64_t n,

@@ -36,7 +36,7 @@ def emu():
     srcs = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_emu.h"),
             os.path.join(ROOT, "datasketch_b200", "csrc", "minhash_kernels.cu"),
             os.path.join(ROOT, "datasketch_b200", "csrc", "dsk_common.cuh")] + [
-                os.path.join(ROOT, "datasketch_b200", "csrc", f + "_kernels.cu") for f in ("codec", "lsh", "jaccard", "sha1", "wmh")]
+                os.path.join(ROOT, "datasketch_b200", "csrc", f + "_kernels.cu") for f in ("codec", "lsh", "jaccard", "sha1", "hash", "wmh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-ffp-contract=off", "-DDSK_EMU", "-I" + EMU, "-shared", "-fPIC", "-o", so,
                         srcs[0]], check=True)
@@ -356,6 +356,23 @@ def test_sha1_kernel_vs_hashlib(emu):
     assert lib.emu_sha1_tokens(_ptr(blob), _ptr(off), ctypes.c_int64(len(toks)), _ptr(h64), 1) == 0
     assert h32.tolist() == [struct.unpack("<I", hashlib.sha1(t).digest()[:4])[0] for t in toks]
     assert h64.tolist() == [struct.unpack("<Q", hashlib.sha1(t).digest()[:8])[0] for t in toks]
+
+
+def test_xxh32_and_murmur3_kernels(emu, golden):
+    """hash_tokens_kernel against the values the `xxhash` package produced (tests/golden/hashes.npz) and, for
+    MurmurHash3, against the oracle restatement (itself pinned to published vectors in test_oracle_golden.py)."""
+    lib = emu.lib
+    g = golden("hashes")
+    blob, off = np.ascontiguousarray(g["blob"]), np.ascontiguousarray(g["off"])
+    n = len(off) - 1
+    blob = np.concatenate([blob, np.zeros(8, np.uint8)])
+    for seed in (0, 1, 0x9747B28C):
+        out = np.zeros(n, dtype=np.uint32)
+        assert lib.emu_hash_tokens(_ptr(blob), _ptr(off), ctypes.c_int64(n), 1, ctypes.c_uint32(seed), _ptr(out)) == 0
+        assert np.array_equal(out, g[f"xxh32_seed{seed}"])
+        assert lib.emu_hash_tokens(_ptr(blob), _ptr(off), ctypes.c_int64(n), 2, ctypes.c_uint32(seed), _ptr(out)) == 0
+        want = [o.murmur3_32(bytes(blob[off[i]:off[i + 1]]), seed) for i in range(n)]
+        assert out.tolist() == want
 
 
 @pytest.mark.parametrize("tag", ["small", "tiny"])

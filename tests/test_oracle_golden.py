@@ -175,3 +175,29 @@ def test_wmh_minhash_many(golden):
         o.wmh_minhash_many(np.ones(5), *o.wmh_params(5, 4, 1))
     with pytest.raises(ValueError):
         o.wmh_minhash_many(np.ones((2, 3)), *o.wmh_params(5, 4, 1))
+
+
+def test_token_hashes(golden):
+    """xxh32 restatement vs the values the `xxhash` package produced; MurmurHash3 x86_32 vs published vectors
+    (SMHasher / mmh3 documentation); the product's single-token host functions agree with both."""
+    from datasketch_b200 import hashfunc as hf
+    g = golden("hashes")
+    blob, off = g["blob"], g["off"]
+    toks = [bytes(blob[off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+    for seed in (0, 1, 0x9747B28C):
+        want = g[f"xxh32_seed{seed}"].tolist()
+        assert [o.xxh32(t, seed) for t in toks] == want
+        assert [hf.xxh32_hash32(t, seed) for t in toks] == want
+    vectors = {(b"", 0): 0, (b"", 1): 0x514E28B7, (b"", 0xFFFFFFFF): 0x81F16F39, (b"\xff\xff\xff\xff", 0): 0x76293B50,
+               (b"!Ce\x87", 0): 0xF55B516B, (b"!Ce\x87", 0x5082EDEE): 0x2362F9DE, (b"!Ce", 0): 0x7E4A8634,
+               (b"!C", 0): 0xA0F7B07A, (b"!", 0): 0x72661CF4, (b"\0\0\0\0", 0): 0x2362F9DE, (b"aaaa", 0x9747B28C): 0x5A97808A,
+               (b"hello", 0): 0x248BFA47, (b"foo", 0): 0xF6A5C420, (b"Hello, world!", 0): 0xC0363E43,
+               (b"The quick brown fox jumps over the lazy dog", 0): 0x2E4FF723}
+    for (data, seed), want in vectors.items():
+        assert o.murmur3_32(data, seed) == want and hf.murmur3_hash32(data, seed) == want, (data, seed)
+    rs = np.random.RandomState(5)
+    for _ in range(200):
+        d = bytes(rs.randint(0, 256, size=rs.randint(0, 70)).astype(np.uint8))
+        s32 = int(rs.randint(0, 1 << 32))
+        assert hf.murmur3_hash32(d, s32) == o.murmur3_32(d, s32) and hf.xxh32_hash32(d, s32) == o.xxh32(d, s32)
+    assert hf.sha1_hash32(b"Hello") == o.sha1_hash32(b"Hello")
