@@ -2,7 +2,8 @@
 partition bounds, (b, r) tables, and the query results of an indexed corpus.
 
 The CPU tests inject the oracle's band keys into ``MinHashLSH._batch_band_keys`` (this container has no GPU);
-the GPU test runs the product path (one ``dsk_band_keys`` launch per partition and r)."""
+the GPU run of the same check (product path: one ``dsk_band_keys`` launch per partition and r) lives in
+tests/test_zz_first_gpu_run.py."""
 import numpy as np
 import pytest
 
@@ -49,7 +50,7 @@ def test_constructor_and_index_errors(dsk):
         e.index(iter([("a", m, 0)]))                 # "Set size must be positive" (checked for non-list input)
 
 
-def _index_and_check(dsk, g):
+def index_and_check(dsk, g):
     thr, k, num_part, m = g["e2e_cfg"]
     sig, sizes = g["e2e_sig"], g["e2e_sizes"]
     mhs = [dsk.MinHash(num_perm=int(k), seed=1, hashvalues=row.astype(np.uint64)) for row in sig]
@@ -70,9 +71,5 @@ def test_index_query_match_reference_with_oracle_band_keys(dsk, golden, monkeypa
     def oracle_keys(self, sig):
         return [o.lsh_band_keys(row.astype(np.uint64), self.b, self.r) for row in sig]
     monkeypatch.setattr(dsk.MinHashLSH, "_batch_band_keys", oracle_keys)
-    _index_and_check(dsk, golden("ensemble"))
+    index_and_check(dsk, golden("ensemble"))
 
-
-@pytest.mark.gpu
-def test_index_query_match_reference_gpu(dsk, golden):
-    _index_and_check(dsk, golden("ensemble"))
