@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Optional, Sequence, Tuple
 
+import threading
+
 import numpy as np
 
 from . import _native as nv
@@ -122,6 +124,7 @@ def bulk_signatures_device(d_tokens, d_offsets, n_tokens: int, permutations: np.
 
 
 _stage: dict = {}
+_stage_lock = threading.Lock()   # the pinned staging buffers are shared: one bulk_signatures_sha1 call at a time
 
 
 def _pinned_stage(name: str, nbytes: int):
@@ -196,55 +199,56 @@ def bulk_signatures_sha1(docs: Sequence[Sequence[bytes]], permutations: np.ndarr
     cache-hot) plus one ``map(len, ...)`` over all tokens; a token that is not bytes-like raises
     TypeError before anything reaches the device (the caller then takes the per-token hashfunc
     route, which raises what the reference raises)."""
-    import itertools
-    import torch
-    nv.require_device(device)
-    dev = torch.device("cuda", device)
-    n = len(docs)
-    doc_lens = np.fromiter(map(len, docs), dtype=np.int64, count=n)
-    off = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(doc_lens, out=off[1:])
-    n_tok = int(off[-1])
-    lens = np.fromiter(map(len, itertools.chain.from_iterable(docs)), dtype=np.int64, count=n_tok)
-    # grow-only pinned staging (no fresh-page faults per call, full-rate H2D); safe to reuse because this
-    # function returns only after the device->host copy of the result, which is ordered after both uploads
-    h_boff = _pinned_stage("boff", (n_tok + 1) * 8).view(torch.int64).numpy()
-    h_boff[0] = 0
-    np.cumsum(lens, out=h_boff[1:n_tok + 1])
-    total = int(h_boff[n_tok])
-    h_blob = _pinned_stage("blob", total)
-    mv = memoryview(h_blob.numpy())
-    pos = 0
-    for d in docs:
-        piece = b"".join(d)  # TypeError for a token that is not bytes-like
-        end = pos + len(piece)
-        if end > total:
-            break
-        mv[pos:end] = piece
-        pos = end
-    else:
-        end = pos
-    if end != total:  # e.g. array('I') tokens: len() counts items, not bytes
-        raise TypeError("tokens must be byte strings (item size 1)")
-    d_bytes = torch.empty((max(total, 1),), dtype=torch.uint8, device=dev)
-    d_bytes[:total].copy_(h_blob[:total], non_blocking=True)
-    d_boff = torch.empty((n_tok + 1,), dtype=torch.int64, device=dev)
-    d_boff.copy_(_pinned_stage("boff", 0).view(torch.int64)[:n_tok + 1], non_blocking=True)
-    d_hash = torch.empty((max(n_tok, 4),), dtype=torch.int32, device=dev)
-    with torch.cuda.device(device):
-        st = torch.cuda.current_stream(dev).cuda_stream
-        if hash_kind == 0:
-            nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, d_hash.data_ptr(), 0, st))
+    with _stage_lock:
+        import itertools
+        import torch
+        nv.require_device(device)
+        dev = torch.device("cuda", device)
+        n = len(docs)
+        doc_lens = np.fromiter(map(len, docs), dtype=np.int64, count=n)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(doc_lens, out=off[1:])
+        n_tok = int(off[-1])
+        lens = np.fromiter(map(len, itertools.chain.from_iterable(docs)), dtype=np.int64, count=n_tok)
+        # grow-only pinned staging (no fresh-page faults per call, full-rate H2D); safe to reuse because this
+        # function returns only after the device->host copy of the result, which is ordered after both uploads
+        h_boff = _pinned_stage("boff", (n_tok + 1) * 8).view(torch.int64).numpy()
+        h_boff[0] = 0
+        np.cumsum(lens, out=h_boff[1:n_tok + 1])
+        total = int(h_boff[n_tok])
+        h_blob = _pinned_stage("blob", total)
+        mv = memoryview(h_blob.numpy())
+        pos = 0
+        for d in docs:
+            piece = b"".join(d)  # TypeError for a token that is not bytes-like
+            end = pos + len(piece)
+            if end > total:
+                break
+            mv[pos:end] = piece
+            pos = end
         else:
-            nv.check(nv.load().dsk_hash_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, int(hash_kind), 0,
-                                                d_hash.data_ptr(), st))
-    d_off = torch.from_numpy(off).to(dev)
-    d_out = torch.empty((n, permutations.shape[1]), dtype=torch.int64, device=dev)
-    d_init, stride = None, 0
-    if init is not None:
-        init = np.ascontiguousarray(init, dtype=np.uint64)
-        d_init = torch.from_numpy(init.view(np.int64)).to(dev)
-        stride = 0 if init.ndim == 1 else init.shape[1]
-    if n:
-        bulk_signatures_device(d_hash, d_off, n_tok, permutations, d_out=d_out, d_init=d_init, init_stride=stride)
-    return d_out.cpu().numpy().view(np.uint64)
+            end = pos
+        if end != total:  # e.g. array('I') tokens: len() counts items, not bytes
+            raise TypeError("tokens must be byte strings (item size 1)")
+        d_bytes = torch.empty((max(total, 1),), dtype=torch.uint8, device=dev)
+        d_bytes[:total].copy_(h_blob[:total], non_blocking=True)
+        d_boff = torch.empty((n_tok + 1,), dtype=torch.int64, device=dev)
+        d_boff.copy_(_pinned_stage("boff", 0).view(torch.int64)[:n_tok + 1], non_blocking=True)
+        d_hash = torch.empty((max(n_tok, 4),), dtype=torch.int32, device=dev)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            if hash_kind == 0:
+                nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, d_hash.data_ptr(), 0, st))
+            else:
+                nv.check(nv.load().dsk_hash_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n_tok, int(hash_kind), 0,
+                                                    d_hash.data_ptr(), st))
+        d_off = torch.from_numpy(off).to(dev)
+        d_out = torch.empty((n, permutations.shape[1]), dtype=torch.int64, device=dev)
+        d_init, stride = None, 0
+        if init is not None:
+            init = np.ascontiguousarray(init, dtype=np.uint64)
+            d_init = torch.from_numpy(init.view(np.int64)).to(dev)
+            stride = 0 if init.ndim == 1 else init.shape[1]
+        if n:
+            bulk_signatures_device(d_hash, d_off, n_tok, permutations, d_out=d_out, d_init=d_init, init_stride=stride)
+        return d_out.cpu().numpy().view(np.uint64)
