@@ -9,6 +9,7 @@
 #include <pthread.h>
 #include <sched.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <math.h>
@@ -78,8 +79,39 @@ static inline int atomicCAS(int *p, int cmp, int val) {
 static inline int atomicExch(int *p, int val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
+// ---- CUDA runtime, synchronous and on host memory: "device" pointers are host pointers, one fake device with two SMs
+enum { cudaErrorMemoryAllocation = 2, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100 };
+enum { cudaStreamNonBlocking = 1 };
+struct cudaDeviceProp { int multiProcessorCount, major, minor; size_t totalGlobalMem; char name[64]; };
+static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorNoDevice; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+    memset(p, 0, sizeof(*p));
+    p->multiProcessorCount = 2; p->major = 10; p->minor = 0; p->totalGlobalMem = (size_t)8 << 30;
+    strcpy(p->name, "emulated sm_100 (host threads)");
+    return cudaSuccess;
+}
+template <typename T>
+static inline cudaError_t cudaMalloc(T **p, size_t n) {
+    *p = static_cast<T *>(aligned_alloc(256, (n + 255) / 256 * 256 + 256));
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+template <typename T>
+static inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 static inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) {
+    memcpy(dst, src, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) {
     memcpy(dst, src, n);
     return cudaSuccess;
 }
