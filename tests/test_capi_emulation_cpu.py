@@ -29,25 +29,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 
 
-@pytest.fixture(scope="module")
-def emu_lib():
-    from datasketch_b200 import _native as nv
-    out = os.path.join(EMU, "_build")
-    os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libdsk_emu.so")
-    csrc = os.path.join(ROOT, "datasketch_b200", "csrc")
-    srcs = [os.path.join(EMU, "emu_capi.cpp"), os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "include", "dsk.h")] + \
-           [os.path.join(csrc, f) for f in os.listdir(csrc)]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-ffp-contract=off", "-DDSK_EMU", "-I" + EMU, "-shared",
-                        "-fPIC", "-o", so, srcs[0]], check=True)
-    lib = ctypes.CDLL(so)
-    for name, (res, args) in nv.SIGNATURES.items():
-        fn = getattr(lib, name)               # the emulated build exports every C-ABI symbol too
-        fn.restype, fn.argtypes = res, args
-    return lib
-
-
 @pytest.fixture()
 def dsk_on_emu(emu_lib, monkeypatch):
     """datasketch_b200 with the emulated library swapped in for libdsk_b200.so (host-buffer paths only)."""
