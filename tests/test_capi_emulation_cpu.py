@@ -124,3 +124,37 @@ def test_minhash_parity_tests_run_on_the_emulated_library(dsk_on_emu, golden):
 def test_api_fuzz_runs_on_the_emulated_library(dsk_on_emu):
     import test_minhash_gpu as t
     t.test_api_fuzz_against_oracle(dsk_on_emu)
+
+
+def test_device_entry_points_and_fused_gather(emu_lib):
+    """dsk_minhash_bulk (device-pointer entry: alignment check, init) and dsk_minhash_bulk_gather: every signature row
+    must land at row_offset + i of EVERY peer matrix (the peers are plain host buffers here)."""
+    lib = emu_lib
+    rs = np.random.RandomState(3)
+    k, n = 128, 90
+    P = o.init_permutations(k, 1)
+    a, b = np.ascontiguousarray(P[0]), np.ascontiguousarray(P[1])
+    h = ctypes.c_void_p()
+    assert lib.dsk_perm_create(a.ctypes.data, b.ctypes.data, k, 0, ctypes.byref(h)) == 0
+    lens = rs.randint(0, 120, size=n)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]) + 4, dtype=np.uint64).astype(np.uint32)
+    want = oc.minhash_bulk_u32tok(tok[:off[-1]], off, P)
+    out = np.zeros((n, k), dtype=np.uint32)
+    assert lib.dsk_minhash_bulk(h, tok.ctypes.data, 0, off.ctypes.data, n, int(off[-1]), None, 0, 0, out.ctypes.data, 0, 0,
+                                None) == 0, lib.dsk_last_error()
+    assert np.array_equal(out, want)
+    assert lib.dsk_minhash_bulk(h, tok.ctypes.data + 4, 0, off.ctypes.data, n, int(off[-1]) - 1, None, 0, 0, out.ctypes.data,
+                                0, 0, None) != 0                      # token pointer not 16-byte aligned
+    assert b"align" in lib.dsk_last_error().lower()
+    n_total, row0 = n + 37, 20
+    peers = [np.full((n_total, k), 0xABCDEF01, dtype=np.uint32) for _ in range(3)]
+    ptrs = (ctypes.c_void_p * 3)(*[p.ctypes.data for p in peers])
+    assert lib.dsk_minhash_bulk_gather(h, tok.ctypes.data, 0, off.ctypes.data, n, int(off[-1]), ptrs, 3, row0, 0, 0,
+                                       None) == 0, lib.dsk_last_error()
+    for p in peers:
+        assert np.array_equal(p[row0:row0 + n], want)
+        assert (p[:row0] == 0xABCDEF01).all() and (p[row0 + n:] == 0xABCDEF01).all()   # nothing else touched
+    assert lib.dsk_minhash_bulk_gather(h, tok.ctypes.data, 0, off.ctypes.data, n, int(off[-1]), ptrs, 9, row0, 0, 0, None) != 0
+    lib.dsk_perm_destroy(h)
