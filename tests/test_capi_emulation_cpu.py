@@ -158,3 +158,96 @@ def test_device_entry_points_and_fused_gather(emu_lib):
         assert (p[:row0] == 0xABCDEF01).all() and (p[row0 + n:] == 0xABCDEF01).all()   # nothing else touched
     assert lib.dsk_minhash_bulk_gather(h, tok.ctypes.data, 0, off.ctypes.data, n, int(off[-1]), ptrs, 9, row0, 0, 0, None) != 0
     lib.dsk_perm_destroy(h)
+
+
+def test_remaining_entry_points_through_the_c_abi(emu_lib, golden):
+    """One pass over every other C-ABI entry with host buffers standing in for device buffers: results against the oracle
+    / fixtures, and the argument checks each entry makes."""
+    lib = emu_lib
+    P64, I64 = ctypes.c_void_p, ctypes.c_int64
+    rs = np.random.RandomState(10)
+    ptr = lambda x: P64(x.ctypes.data)                                              # noqa: E731
+    # permutation analysis (host-only entry)
+    P = o.init_permutations(64, 2)
+    bad = np.ones(64, dtype=np.uint8)
+    assert lib.dsk_perm_analyze(ptr(np.ascontiguousarray(P[0])), ptr(np.ascontiguousarray(P[1])), 64, ptr(bad)) == 0
+    assert not bad.any()
+    # merge, lean codec, band keys / fingerprints, b-bit
+    k, n = 128, 50
+    sig = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    other = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    out = np.zeros_like(sig)
+    assert lib.dsk_sig_merge_min(ptr(sig), ptr(other), I64(n * k), ptr(out), None) == 0
+    assert np.array_equal(out, np.minimum(sig, other))
+    rec = np.zeros((n, 12 + 4 * k), dtype=np.uint8)
+    assert lib.dsk_lean_pack(ptr(sig), 0, I64(n), k, I64(-5), 0, ptr(rec), None) == 0
+    assert np.array_equal(rec, oc.lean_pack_le(sig, -5))
+    back = np.zeros_like(sig)
+    st = np.zeros(1, dtype=np.int32)
+    assert lib.dsk_lean_unpack(ptr(rec), I64(n), k, I64(-5), 0, ptr(back), 0, ptr(st), None) == 0
+    assert st[0] == 0 and np.array_equal(back, sig)
+    keys = np.zeros((n, 9, 8 * 13), dtype=np.uint8)
+    assert lib.dsk_band_keys(ptr(sig), I64(n), k, 9, 13, ptr(keys), None) == 0
+    assert np.array_equal(keys, oc.band_keys_be(sig, 9, 13))
+    assert lib.dsk_band_keys(ptr(sig), I64(n), k, 20, 13, ptr(keys), None) != 0           # b * r > num_perm
+    fp = np.zeros((n, 9), dtype=np.uint64)
+    assert lib.dsk_band_fingerprints(ptr(sig), I64(n), k, 9, 13, ptr(fp), None) == 0 and len(np.unique(fp)) == fp.size
+    blocks = np.zeros((n, k // 16), dtype=np.uint64)
+    assert lib.dsk_bbit_pack(ptr(sig), I64(n), k, 3, ptr(blocks), None) == 0               # b = 3 -> 4-bit slots
+    unp = np.zeros_like(sig)
+    assert lib.dsk_bbit_unpack(ptr(blocks), I64(n), k, 3, ptr(unp), None) == 0 and np.array_equal(unp, sig & 7)
+    assert lib.dsk_bbit_pack(ptr(sig), I64(n), k, 40, ptr(blocks), None) != 0
+    # Jaccard
+    low = rs.randint(0, 3, size=(200, 64)).astype(np.uint32)
+    ia, ib = rs.randint(0, 200, size=300).astype(np.int64), rs.randint(0, 200, size=300).astype(np.int64)
+    cnt = np.zeros(300, dtype=np.int32)
+    assert lib.dsk_jaccard_pairs(ptr(low), I64(200), 64, ptr(ia), ptr(ib), I64(300), ptr(cnt), None) == 0
+    assert np.array_equal(cnt, (low[ia] == low[ib]).sum(axis=1))
+    tc, ti = np.zeros((200, 4), dtype=np.int32), np.zeros((200, 4), dtype=np.int64)
+    assert lib.dsk_jaccard_topk(ptr(low), I64(200), ptr(low), I64(200), 64, 4, I64(0), ptr(tc), ptr(ti), None) == 0
+    c0 = (low == low[0][None, :]).sum(axis=1)
+    order = np.lexsort((np.arange(200), -c0))
+    order = order[order != 0][:4]
+    assert np.array_equal(ti[0], order) and np.array_equal(tc[0], c0[order])
+    assert lib.dsk_jaccard_topk(ptr(low), I64(200), ptr(low), I64(200), 64, 99, I64(0), ptr(tc), ptr(ti), None) != 0
+    # LSH index handle
+    ix = ctypes.c_void_p()
+    assert lib.dsk_lsh_create(64, 8, 8, I64(200), 0, ctypes.byref(ix)) == 0
+    assert lib.dsk_lsh_create(64, 9, 8, I64(200), 0, ctypes.byref(ctypes.c_void_p())) != 0     # b * r > num_perm
+    assert lib.dsk_lsh_insert(ix, ptr(low), I64(200), None) == 0
+    assert lib.dsk_lsh_insert(ix, ptr(low), I64(1), None) != 0 and b"capacity" in lib.dsk_last_error()
+    nd, cap = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.dsk_lsh_size(ix, ctypes.byref(nd), ctypes.byref(cap)) == 0 and (nd.value, cap.value) == (200, 200)
+    counts = np.zeros(201, dtype=np.int64)
+    assert lib.dsk_lsh_query_count(ix, ptr(low), I64(200), ptr(counts), None) == 0
+    pref, scratch = np.zeros(201, dtype=np.int64), np.zeros(8, dtype=np.int64)
+    assert lib.dsk_exclusive_scan(ptr(counts), I64(200), ptr(pref), ptr(scratch), None) == 0
+    idx = np.zeros(max(int(pref[-1]), 1), dtype=np.int32)
+    assert lib.dsk_lsh_query_fill(ix, ptr(low), I64(200), ptr(pref), ptr(idx), None) == 0
+    ref = o.DictLSH(64, 8, 8)
+    for i, row in enumerate(low):
+        ref.insert(i, row.astype(np.uint64))
+    for j in (0, 57, 199):
+        assert sorted(idx[pref[j]:pref[j + 1]].tolist()) == sorted(ref.query(low[j].astype(np.uint64)))
+    lib.dsk_lsh_destroy(ix)
+    # token hashes and Weighted MinHash
+    g = golden("hashes")
+    blob, off = np.concatenate([g["blob"], np.zeros(8, np.uint8)]), np.ascontiguousarray(g["off"])
+    nt = len(off) - 1
+    h32 = np.zeros(nt, dtype=np.uint32)
+    assert lib.dsk_hash_tokens(ptr(blob), ptr(off), I64(nt), 1, 1, ptr(h32), None) == 0
+    assert np.array_equal(h32, g["xxh32_seed1"])
+    assert lib.dsk_sha1_tokens(ptr(blob), ptr(off), I64(nt), ptr(h32), 0, None) == 0
+    assert h32[3] == o.sha1_hash32(bytes(blob[off[3]:off[4]]))
+    w = golden("wmh")
+    dim, ss, seed = (int(x) for x in w["tiny_cfg"])
+    rs_, ln_cs, betas = (np.ascontiguousarray(x) for x in o.wmh_params(dim, ss, seed))
+    gen = ctypes.c_void_p()
+    assert lib.dsk_wmh_create(ptr(rs_), ptr(ln_cs), ptr(betas), ss, dim, 0, ctypes.byref(gen)) == 0
+    V = np.ascontiguousarray(w["tiny_v"], dtype=np.float32)
+    kt = np.zeros((len(V), ss, 2), dtype=np.int64)
+    stv = np.zeros(len(V), dtype=np.int32)
+    assert lib.dsk_wmh_minhash(gen, ptr(V), I64(len(V)), ptr(kt), ptr(stv), 0, None) == 0
+    assert not stv.any() and np.array_equal(kt, w["tiny_out"])
+    assert lib.dsk_wmh_minhash(gen, ptr(V), I64(len(V)), ptr(kt), ptr(stv), 5, None) != 0      # unknown flags
+    lib.dsk_wmh_destroy(gen)
