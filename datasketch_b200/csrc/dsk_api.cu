@@ -104,7 +104,7 @@ struct dsk_perm {
     int num_perm = 0;
     int kpad = 0;
     int n_unsafe = 0;
-    uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi, each kpad entries
+    uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi | b_lo + 7, each kpad entries
     unsigned *d_counters = nullptr;  // kCounterSets x kCounterStride work counters (one set per in-flight launch)
     mutable std::atomic<unsigned> next_set{0};
     std::vector<uint64_t> a, b;
@@ -170,7 +170,7 @@ int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int 
     p->kpad = (num_perm + 255) / 256 * 256;
     p->a.assign(h_a, h_a + num_perm);
     p->b.assign(h_b, h_b + num_perm);
-    std::vector<uint32_t> tab((size_t)4 * p->kpad, 0u);
+    std::vector<uint32_t> tab((size_t)5 * p->kpad, 0u);
     for (int i = 0; i < num_perm; ++i) {
         tab[i] = (uint32_t)h_a[i];
         tab[p->kpad + i] = (uint32_t)(h_a[i] >> 32);
@@ -185,6 +185,7 @@ int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int 
         const int src = i % num_perm;
         for (int q = 0; q < 4; ++q) tab[(size_t)q * p->kpad + i] = tab[(size_t)q * p->kpad + src];
     }
+    for (int i = 0; i < p->kpad; ++i) tab[(size_t)4 * p->kpad + i] = tab[(size_t)2 * p->kpad + i] + 7u;
     int prev = 0;
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
@@ -285,6 +286,7 @@ int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u6
     prm.a_hi = perm->d_tab + perm->kpad;
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
     prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
     prm.k = perm->num_perm;
     prm.init = d_init;
     prm.init_stride = init_stride;
@@ -292,7 +294,7 @@ int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u6
     prm.out = d_out;
     prm.out_is_u64 = out_is_u64;
     prm.work_counter = perm_counters(perm);
-    prm.docs_per_unit = 1;
+    prm.docs_per_unit = 0;
     prm.n_peers = 0;
     prm.peer_row_offset = 0;
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
@@ -327,6 +329,7 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
     prm.a_hi = perm->d_tab + perm->kpad;
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
     prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
     prm.k = perm->num_perm;
     prm.init = nullptr;
     prm.init_stride = 0;
@@ -334,7 +337,7 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
     prm.out = nullptr;
     prm.out_is_u64 = out_is_u64;
     prm.work_counter = perm_counters(perm);
-    prm.docs_per_unit = 1;
+    prm.docs_per_unit = 0;
     prm.n_peers = n_peers;
     prm.peer_row_offset = row_offset;
     for (int i = 0; i < 8; ++i) prm.peer_out[i] = i < n_peers ? h_peer_out[i] : nullptr;
@@ -912,6 +915,7 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
     prm.a_hi = perm->d_tab + perm->kpad;
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
     prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
     prm.k = K;
     prm.init = nullptr;
     prm.init_stride = init_stride;
@@ -968,7 +972,7 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         prm.n_docs = n_ext;
         prm.n_tokens = nt;
         prm.work_counter = perm_counters(perm);
-        prm.docs_per_unit = 1;
+        prm.docs_per_unit = 0;
         prm.n_peers = 0;
         prm.peer_row_offset = 0;
         if (!split) {

@@ -41,7 +41,8 @@ struct BulkParams {
     const void *tokens;         // u32 or u64 token hashes, 16-byte aligned
     const int64_t *offsets;     // [n_docs + 1] CSR offsets relative to `tokens`
     int64_t n_docs, n_tokens;
-    const uint32_t *a_lo, *a_hi, *b_lo, *b_hi;  // permutation halves, zero-padded to a multiple of 256
+    const uint32_t *a_lo, *a_hi, *b_lo, *b_hi;  // permutation halves, padded to a multiple of 256 (padding repeats real ones)
+    const uint32_t *b_lo7;      // b_lo + 7 (mod 2^32): the addend of the two-phase kernel's cheap value L'
     int k;                      // num_perm
     const void *init;           // running signatures to merge, or nullptr
     int64_t init_stride;        // elements between init rows (0 = broadcast one row)
@@ -49,7 +50,7 @@ struct BulkParams {
     void *out;                  // [n_docs, k] u32 or u64
     int out_is_u64;
     unsigned *work_counter;     // [K slices] device counters, zeroed by the launcher: dynamic unit distribution
-    int docs_per_unit;          // set by the launcher
+    int docs_per_unit;          // 0 = chosen by the launcher; > 0 = forced (tests)
     // fused all-gather epilogue: when n_peers > 0 every signature row is stored into each peer_out[p]
     // (the full [N_total, k] matrix of rank p, mapped peer memory) at row peer_row_offset + d
     int n_peers;
@@ -58,6 +59,7 @@ struct BulkParams {
 };
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
+cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s);   // signature_kernel.cu (two-phase)
 cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
                            int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,
                            cudaStream_t s);

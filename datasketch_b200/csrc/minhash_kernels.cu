@@ -76,10 +76,7 @@ template <> struct TokLoad<uint64_t> {
     }
 };
 
-// RESCAN selects the exact re-scan used when several blocks fall inside a permutation's +7 window (repeated
-// tokens do that): 0 = per-token clamped loads (the round-1 validated path), 1 = whole blocks by four broadcast
-// LDG.128 with the tokens kept in registers (experimental, opt-in via DSK_RESCAN=1).
-template <int P, int MODE, typename TokT, int OCC, int RESCAN = 0>
+template <int P, int MODE, typename TokT, int OCC>
 __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const BulkParams prm) {
     static_assert(MODE == MODE_EXACT || sizeof(TokT) == 4, "fast paths need 32-bit token hashes");
     constexpr int kBlkBytes = kBlkTok * (int)sizeof(TokT);
@@ -383,63 +380,7 @@ __global__ void __launch_bounds__(kWarps * 32, OCC) minhash_bulk_kernel(const Bu
                     }
                 }
             }
-            if constexpr (RESCAN == 1) {
-                if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
-                    uint32_t rs[P];
-#pragma unroll
-                    for (int j = 0; j < P; ++j) rs[j] = 0xFFFFFFFFu;
-                    const int64_t b_first = start / kBlkTok, b_last = (end - 1) / kBlkTok;
-                    const bool head_cut = (start % kBlkTok) != 0, tail_cut = (end % kBlkTok) != 0;
-                    auto partial = [&](int64_t blk) { return (blk == b_first && head_cut) || (blk == b_last && tail_cut); };
-                    // whole blocks are fetched one block ahead (four broadcast LDG.128, same address on every lane),
-                    // so the L2 latency of block i+1 overlaps the evaluation of block i
-                    uint4 nxt[4];
-                    auto fetch = [&](int64_t blk) {
-                        const uint4 *q = reinterpret_cast<const uint4 *>(tokens + blk * kBlkTok);   // 64-byte aligned
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) nxt[i] = __ldg(q + i);
-                    };
-                    if (!partial(b_first)) fetch(b_first);
-                    for (int64_t blk = b_first; blk <= b_last; ++blk) {
-                        uint32_t t[kBlkTok];
-                        const int64_t base = blk * kBlkTok;
-                        if (partial(blk)) {
-                            // boundary block: out-of-document slots duplicate an in-document token
-#pragma unroll
-                            for (int i = 0; i < kBlkTok; ++i)
-                                t[i] = (uint32_t)__ldg(tokens + max(start, min(base + i, end - 1)));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                t[4 * i] = nxt[i].x; t[4 * i + 1] = nxt[i].y; t[4 * i + 2] = nxt[i].z; t[4 * i + 3] = nxt[i].w;
-                            }
-                        }
-                        if (blk + 1 <= b_last && !partial(blk + 1)) fetch(blk + 1);
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            if (!((need_slow >> j) & 1u)) continue;
-                            const uint32_t c7 = blo[j] + 7u;
-                            uint32_t bm = umin3(alo[j] * t[0] + c7, alo[j] * t[1] + c7, alo[j] * t[2] + c7);
-#pragma unroll
-                            for (int i = 3; i < kBlkTok - 1; i += 2)
-                                bm = umin3(bm, alo[j] * t[i] + c7, alo[j] * t[i + 1] + c7);
-                            bm = min(bm, alo[j] * t[kBlkTok - 1] + c7);
-                            // m is the minimum of these same block minima, so bm - m cannot wrap
-                            if (m[j] < 7u || (bm - m[j]) <= 7u) {
-                                const uint64_t b64 = ((uint64_t)bhi[j] << 32) | blo[j];
-                                uint32_t r = rs[j];
-#pragma unroll
-                                for (int i = 0; i < kBlkTok; i += 2)
-                                    r = umin3(r, eval_fast(alo[j], ahi[j], b64, t[i]), eval_fast(alo[j], ahi[j], b64, t[i + 1]));
-                                rs[j] = r;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < P; ++j)
-                        if ((need_slow >> j) & 1u) res[j] = rs[j];
-                }
-            } else if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
+            if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
                 uint32_t rs[P];
 #pragma unroll
                 for (int j = 0; j < P; ++j) rs[j] = 0xFFFFFFFFu;
@@ -561,7 +502,7 @@ cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_d
 }
 
 // ---- launchers --------------------------------------------------------------------------------
-template <int P, int MODE, typename TokT, int OCC, int RESCAN = 0>
+template <int P, int MODE, typename TokT, int OCC>
 static cudaError_t launch_bulk(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
     BulkParams prm = prm_in;
     const int slices = (prm.k + 32 * P - 1) / (32 * P);
@@ -571,64 +512,38 @@ static cudaError_t launch_bulk(const BulkParams &prm_in, int sm_count, cudaStrea
     if (gx > gmax) gx = gmax;
     if (gx < 1) gx = 1;
     // unit size: ~8 units per warp for balance, at most 32 documents so a unit's ring restart is amortised
-    int64_t dpu = prm.n_docs / (gx * kWarps * 8);
-    prm.docs_per_unit = (int)(dpu < 1 ? 1 : (dpu > 32 ? 32 : dpu));
+    if (prm.docs_per_unit <= 0) {   // 0 = choose here; > 0 = forced by the caller (tests)
+        int64_t dpu = prm.n_docs / (gx * kWarps * 8);
+        prm.docs_per_unit = (int)(dpu < 1 ? 1 : (dpu > 32 ? 32 : dpu));
+    }
     cudaError_t e = cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned) * (size_t)slices, s);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)gx, (unsigned)slices);
-    DSK_LAUNCH((minhash_bulk_kernel<P, MODE, TokT, OCC, RESCAN>), grid, kWarps * 32, 0, s, prm);
+    DSK_LAUNCH((minhash_bulk_kernel<P, MODE, TokT, OCC>), grid, kWarps * 32, 0, s, prm);
     return cudaGetLastError();
 }
 
-// experimental re-scan variant (see the kernel's RESCAN parameter); off unless DSK_RESCAN=1
-static bool lean_rescan() {
-    static const bool on = [] { const char *e = getenv("DSK_RESCAN"); return e && atoi(e) == 1; }();
+// The round-1 two-phase kernel (MODE_TWO_PHASE of minhash_bulk_kernel) stays selectable for A/B measurements with
+// DSK_TWO_PHASE_V1=1; the default two-phase kernel is minhash_sig_kernel (signature_kernel.cu).
+static bool two_phase_v1() {
+    static const bool on = [] { const char *e = getenv("DSK_TWO_PHASE_V1"); return e && atoi(e) == 1; }();
     return on;
-}
-
-// CTAs per SM the two-phase kernel is compiled for (register cap = 65536 / (128 * OCC)).
-static int two_phase_occ() {
-    static int occ = [] {
-        const char *e = getenv("DSK_TWO_PHASE_OCC");
-        const int v = e ? atoi(e) : 4;
-        return (v == 4 || v == 5 || v == 6) ? v : 4;
-    }();
-    return occ;
 }
 
 template <int MODE, typename TokT>
 static cudaError_t launch_bulk_p(const BulkParams &prm, int sm_count, cudaStream_t s) {
     if (prm.k <= 32) return launch_bulk<1, MODE, TokT, 4>(prm, sm_count, s);
     if (prm.k <= 64) return launch_bulk<2, MODE, TokT, 4>(prm, sm_count, s);
-    if (prm.k <= 128) {
-        if (MODE == MODE_TWO_PHASE) {
-            switch (two_phase_occ()) {
-                case 6: return launch_bulk<4, MODE, TokT, 6>(prm, sm_count, s);
-                case 5: return launch_bulk<4, MODE, TokT, 5>(prm, sm_count, s);
-                default:
-                    if constexpr (MODE == MODE_TWO_PHASE) {
-                        if (lean_rescan()) return launch_bulk<4, MODE, TokT, 4, 1>(prm, sm_count, s);
-                    }
-                    return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);
-            }
-        }
-        return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);
-    }
-    if (MODE == MODE_TWO_PHASE) {
-        // 119 registers, 4 CTAs/SM; measured better than two 128-permutation passes of the P=4 kernel
-        // (K=256: 7.44 vs 7.83 ms for 2M x 128 tokens)
-        if constexpr (MODE == MODE_TWO_PHASE) {
-            if (lean_rescan()) return launch_bulk<8, MODE, TokT, 4, 1>(prm, sm_count, s);
-        }
-        return launch_bulk<8, MODE, TokT, 4>(prm, sm_count, s);
-    }
+    if (prm.k <= 128) return launch_bulk<4, MODE, TokT, 4>(prm, sm_count, s);
+    if (MODE == MODE_TWO_PHASE) return launch_bulk<8, MODE, TokT, 4>(prm, sm_count, s);
     return launch_bulk<8, MODE, TokT, 3>(prm, sm_count, s);
 }
 
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s) {
     if (token_is_u64) return launch_bulk_p<MODE_EXACT, uint64_t>(prm, sm_count, s);
     switch (mode) {
-        case MODE_TWO_PHASE: return launch_bulk_p<MODE_TWO_PHASE, uint32_t>(prm, sm_count, s);
+        case MODE_TWO_PHASE:
+            return two_phase_v1() ? launch_bulk_p<MODE_TWO_PHASE, uint32_t>(prm, sm_count, s) : launch_minhash_sig(prm, sm_count, s);
         case MODE_DIRECT: return launch_bulk_p<MODE_DIRECT, uint32_t>(prm, sm_count, s);
         default: return launch_bulk_p<MODE_EXACT, uint32_t>(prm, sm_count, s);
     }

@@ -1,0 +1,439 @@
+// signature_kernel.cu -- the two-phase signature build (default kernel of dsk_minhash_bulk*), sm_100a.
+//
+// Replaces datasketch/minhash.py:294-297 (numpy) / :281-291 (CuPy) batched over documents as MinHash.bulk
+// does (:464-522).  Arithmetic and exactness argument: DESIGN.md sections 2-3; in short
+//   x = (a*h + b) mod 2^64,  r = lo32(x) + top3(x)      (exact when dsk_perm_create found no unsafe permutation)
+//   L' = lo32(a_lo*h + b_lo + 7)  (one IMAD)  and  r = L' - 7 + top3(x)  lies in [L'-7, L'],
+// so only tokens whose L' is within 7 of a document's smallest L' can carry the minimum.
+//
+// Structure per warp (lane <-> P consecutive permutations, their (a, b) in registers):
+//   stream   units of <= 32 consecutive documents come from a global atomic counter; the unit's token range is
+//            streamed through a per-warp ring of four 1 KB slots by 1-D TMA bulk copies (cp.async.bulk +
+//            mbarrier).  The ring is circular in ABSOLUTE token position: token g lives at ring[g mod 1024].
+//   stage    a document is handled in sub-pieces of <= 512 tokens.  A sub-piece that is 16-byte aligned, a
+//            multiple of 16 tokens long and does not wrap the ring is used in place; any other one is copied
+//            (and re-aligned, padded to a multiple of 16 with a duplicate of its last token -- min is idempotent)
+//            into a per-warp line buffer by the lanes.  When the warp has seen repeated tokens it also DEDUPLICATES
+//            during that copy (a 1024-slot shared-memory hash set, atomicCAS): the signature of a multiset is the
+//            signature of its support, and distinct tokens cannot tie.
+//   phase 1  per 16-token block: 16 IMAD (L') + 8 VIMNMX3 per permutation, then four tracking ops on
+//            key = (block min & ~31) | block index:  m = smallest key, m2 = second smallest.
+//   phase 2  per permutation: recompute L' on the winning block (block index = m & 31), find the one 4-token group
+//            inside the +7 window and evaluate those 4 tokens exactly (groups that hold padding only are ignored).
+//   flagged  a permutation with another block inside the window (m2 - m <= 69), a second group inside the window,
+//            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp: every lane
+//            evaluates r exactly for 1/32 of the sub-piece's tokens under that permutation, then one
+//            redux.sync.min.  Exact for any input; costs ~50 issue slots per flagged (document, permutation).
+#include "dsk_common.cuh"
+
+namespace dsk {
+
+constexpr int kSigWarps = 4;        // warps per CTA
+constexpr int kRingTok = 1024;      // tokens in a warp's ring
+constexpr int kChunkShift = 8;      // 256 tokens = 1 KB per TMA bulk copy / ring slot
+constexpr int kChunkTok = 1 << kChunkShift;
+constexpr int kRingSlots = kRingTok / kChunkTok;
+constexpr int kSubTok = 512;        // tokens per sub-piece
+constexpr int kTabSlots = 1024;     // dedupe hash set (load factor <= 0.5)
+constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
+constexpr uint32_t kKeyMask = 31u;  // low bits of a tracking key hold the block index (32 blocks of 16 tokens)
+constexpr uint32_t kNearWindow = 7u + 2u * kKeyMask;  // m2 - m <= this: another block may be inside the +7 window
+
+// Path counters for the CPU emulation tests (tests/emu): which staging path / how many flagged permutations.
+// The product build compiles them away.
+#ifdef DSK_EMU
+enum { STAT_IN_PLACE = 0, STAT_COPIED, STAT_DEDUPED, STAT_REMOVED, STAT_FLAGGED, STAT_COUNT };
+std::atomic<long long> g_sig_stat[STAT_COUNT];
+#define DSK_SIG_STAT(i, n) do { if (lane == 0) g_sig_stat[i].fetch_add((n), std::memory_order_relaxed); } while (0)
+#else
+#define DSK_SIG_STAT(i, n) do { } while (0)
+#endif
+
+static_assert(kRingSlots == 4, "ring = 4 slots indexed by absolute chunk number & 3");
+static_assert(kSubTok / 16 <= (int)kKeyMask + 1, "block index must fit the key's low bits");
+
+// r = lo32(x) + top3(x)
+__device__ __forceinline__ uint32_t sig_eval(uint32_t alo, uint32_t ahi, uint64_t b, uint32_t h) {
+    uint64_t x = (uint64_t)alo * h + b;                     // IMAD.WIDE.U32
+    uint32_t xh = (uint32_t)(x >> 32) + ahi * h;            // IMAD
+    return (uint32_t)x + (xh >> 29);                        // LEA.HI
+}
+
+__device__ __forceinline__ void load_block16(const uint32_t *src, uint32_t (&t)[16]) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(src);   // four broadcast LDS.128
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 v = q[i];
+        t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+    }
+}
+
+template <int P, int OCC>
+__global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
+    __shared__ __align__(128) uint32_t s_ring[kSigWarps][kRingTok];
+    __shared__ __align__(128) uint32_t s_buf[kSigWarps][kSubTok];
+    __shared__ __align__(16) uint32_t s_tab[kSigWarps][kTabSlots];
+    __shared__ __align__(8) uint64_t s_bar[kSigWarps][kRingSlots];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t *__restrict__ tokens = static_cast<const uint32_t *>(prm.tokens);
+    const int64_t *__restrict__ offsets = prm.offsets;
+    const int K = prm.k;
+    const int kl = blockIdx.y * (32 * P) + lane * P;  // first permutation owned by this lane
+    const int64_t n_docs = prm.n_docs, n_tokens = prm.n_tokens;
+
+    // c7 = b_lo + 7 is what the hot loop adds; b_lo = c7 - 7 is rebuilt where the exact evaluation needs it
+    uint32_t alo[P], ahi[P], c7[P], bhi[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        alo[j] = __ldg(prm.a_lo + kl + j); ahi[j] = __ldg(prm.a_hi + kl + j);
+        // the table holds b_lo + 7 as its own plane: computed here, ptxas re-adds the 7 in every loop iteration
+        c7[j] = __ldg(prm.b_lo7 + kl + j); bhi[j] = __ldg(prm.b_hi + kl + j);
+    }
+
+    uint32_t *const ring = s_ring[warp];
+    uint32_t *const buf = s_buf[warp];
+    uint32_t *const tab = s_tab[warp];
+    uint64_t *const bar = s_bar[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kRingSlots; ++i) mbar_init(&bar[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t par_mask = 0;  // bit s = phase parity the next wait on slot s must use
+
+    // bulk copies move 16-byte granules: the last (n_tokens mod 4) tokens of the array are patched in by lanes
+    const int64_t copy_end_tok = n_tokens & ~(int64_t)3;
+    const int64_t tail_chunk = (copy_end_tok < n_tokens) ? (copy_end_tok >> kChunkShift) : -1;
+
+    bool dedupe = false;     // warp-uniform: copy stage removes repeated tokens
+    int clean_run = 0;       // consecutive deduplicated sub-pieces in which nothing was removed
+
+    while (true) {
+        int64_t unit = 0;
+        if (lane == 0) unit = (int64_t)atomicAdd(prm.work_counter + blockIdx.y, 1u);
+        unit = __shfl_sync(0xFFFFFFFFu, unit, 0);
+        const int64_t dlo = unit * prm.docs_per_unit;
+        if (dlo >= n_docs) break;
+        const int64_t dhi = min(dlo + (int64_t)prm.docs_per_unit, n_docs);
+        const int64_t tok_lo = __ldg(offsets + dlo), tok_hi = __ldg(offsets + dhi);
+        int64_t c_next = tok_lo >> kChunkShift;                 // next chunk to issue
+        int64_t c_wait = c_next;                                // next chunk to wait for
+        const int64_t c_last = (tok_hi - 1) >> kChunkShift;     // last chunk this unit touches (if it has tokens)
+
+        // make tokens [s, e) resident in the ring: chunk c lives in slot c & 3.  Chunks before s's chunk are dead (every
+        // earlier sub-piece is finished), so up to three chunks beyond it can be in flight.
+        auto ensure = [&](int64_t s, int64_t e) {
+            const int64_t cf = s >> kChunkShift, cl = (e - 1) >> kChunkShift;
+            const int64_t lim = min(cf + (kRingSlots - 1), c_last);
+            if (c_next <= lim) {
+                __syncwarp();   // every lane is done reading the chunks these copies overwrite (in-place sub-pieces)
+                if (lane == 0) {
+                    for (int64_t c = c_next; c <= lim; ++c) {
+                        const int slot = (int)(c & (kRingSlots - 1));
+                        const int64_t t0 = c << kChunkShift;
+                        const int64_t t1 = min(t0 + kChunkTok, copy_end_tok);
+                        if (t1 > t0) {
+                            const uint32_t bytes = (uint32_t)(t1 - t0) * 4u;
+                            mbar_arrive_expect_tx(&bar[slot], bytes);
+                            bulk_g2s(ring + slot * kChunkTok, tokens + t0, bytes, &bar[slot]);
+                        } else {
+                            mbar_arrive(&bar[slot]);
+                        }
+                    }
+                }
+                c_next = lim + 1;
+            }
+            while (c_wait <= cl) {
+                const int slot = (int)(c_wait & (kRingSlots - 1));
+                mbar_wait(&bar[slot], (par_mask >> slot) & 1u);
+                par_mask ^= 1u << slot;
+                if (c_wait == tail_chunk) {     // the < 16-byte tail of the whole array cannot travel by bulk copy
+                    const int64_t g = copy_end_tok + lane;
+                    if (g < n_tokens) ring[g & (kRingTok - 1)] = __ldg(tokens + g);
+                    fence_proxy_async();        // generic-proxy write, later bulk copies reuse the slot
+                    __syncwarp();
+                }
+                ++c_wait;
+            }
+        };
+
+        int64_t start = tok_lo;
+        int64_t end_pref = __ldg(offsets + dlo + 1);  // offsets are read one document ahead
+        for (int64_t d = dlo; d < dhi; ++d) {
+            const int64_t end = end_pref;
+            if (d + 1 < dhi) end_pref = __ldg(offsets + d + 2);
+
+            uint32_t acc[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[j] = 0xFFFFFFFFu;
+
+            for (int64_t s = start; s < end; s += kSubTok) {
+                const int len = (int)min((int64_t)kSubTok, end - s);
+                ensure(s, s + len);
+                const uint32_t rpos = (uint32_t)s & (kRingTok - 1);
+
+                // ---- stage: in place, or copy / re-align / pad / deduplicate into the line buffer ----------------
+                const uint32_t *src;
+                int n_eff = len;
+                const bool in_place = !dedupe && (len & 15) == 0 && (rpos & 3u) == 0 && rpos + (uint32_t)len <= (uint32_t)kRingTok;
+                if (in_place) {
+                    src = ring + rpos;
+                    DSK_SIG_STAT(STAT_IN_PLACE, 1);
+                } else {
+                    __syncwarp();   // every lane is done with the previous contents of buf / tab
+                    if (!dedupe) {
+                        for (int i = lane; i < len; i += 32) buf[i] = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
+                        DSK_SIG_STAT(STAT_COPIED, 1);
+                    } else {
+                        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+#pragma unroll
+                        for (int q = 0; q < kTabSlots / 128; ++q)
+                            t4[q * 32 + lane] = make_uint4(kEmptySlot, kEmptySlot, kEmptySlot, kEmptySlot);
+                        __syncwarp();
+                        int base = 0;
+                        for (int i0 = 0; i0 < len; i0 += 32) {
+                            const int i = i0 + lane;
+                            bool keep = i < len;
+                            uint32_t t = 0;
+                            if (keep) {
+                                t = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
+                                if (t != kEmptySlot) {   // (a token equal to the empty marker is simply kept)
+                                    uint32_t slot = (t * 0x9E3779B1u) >> 22;
+                                    while (true) {
+                                        const uint32_t old = atomicCAS(&tab[slot], kEmptySlot, t);
+                                        if (old == kEmptySlot) break;               // first occurrence
+                                        if (old == t) { keep = false; break; }      // seen before
+                                        slot = (slot + 1) & (kTabSlots - 1);
+                                    }
+                                }
+                            }
+                            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                            if (keep) buf[base + __popc(bal & ((1u << lane) - 1u))] = t;
+                            base += __popc(bal);
+                        }
+                        n_eff = base;
+                        DSK_SIG_STAT(STAT_DEDUPED, 1);
+                        DSK_SIG_STAT(STAT_REMOVED, len - n_eff);
+                        clean_run = (n_eff == len) ? clean_run + 1 : 0;
+                        if (clean_run >= 16) { dedupe = false; clean_run = 0; }
+                        __syncwarp();   // buf[n_eff - 1] below was written by another lane
+                    }
+                    const int pad = (16 - (n_eff & 15)) & 15;
+                    if (lane < pad) buf[n_eff + lane] = dedupe || n_eff != len ? buf[n_eff - 1]
+                                                                               : ring[(rpos + (uint32_t)len - 1u) & (kRingTok - 1)];
+                    __syncwarp();
+                    src = buf;
+                }
+                const int nblk = (n_eff + 15) >> 4;
+                const int ngrp = (n_eff + 3) >> 2;   // 4-token groups holding at least one real token
+
+                // ---- phase 1: m = smallest key, m2 = second smallest, key = (block min L' & ~31) | block -------
+                uint32_t m[P], m2[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
+                auto compute = [&](const uint32_t (&t)[16], uint32_t lb) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const uint32_t c = c7[j];
+                        uint32_t bm = umin3(alo[j] * t[0] + c, alo[j] * t[1] + c, alo[j] * t[2] + c);
+#pragma unroll
+                        for (int i = 3; i < 15; i += 2) bm = umin3(bm, alo[j] * t[i] + c, alo[j] * t[i + 1] + c);
+                        bm = min(bm, alo[j] * t[15] + c);
+                        const uint32_t key = (bm & ~kKeyMask) | lb;
+                        const uint32_t om = m[j];
+                        m2[j] = min(m2[j], max(key, om));
+                        m[j] = min(om, key);
+                    }
+                };
+                {
+                    const uint32_t *q = src;
+                    const uint32_t *const qe = src + nblk * 16;
+                    uint32_t lb = 0;
+                    if constexpr (P > 4) {
+#pragma unroll 1
+                        for (; q < qe; q += 16, ++lb) {
+                            uint32_t t[16];
+                            load_block16(q, t);
+                            compute(t, lb);
+                        }
+                    } else {
+                        // software pipeline over two register buffers: the next block's LDS.128 are in flight while
+                        // the current block's IMADs issue
+                        uint32_t ta[16], tb[16];
+                        load_block16(q, ta);
+#pragma unroll 1
+                        while (true) {
+                            const uint32_t *q1 = q + 16;
+                            if (q1 < qe) load_block16(q1, tb);
+                            compute(ta, lb);
+                            if (q1 >= qe) break;
+                            const uint32_t *q2 = q1 + 16;
+                            if (q2 < qe) load_block16(q2, ta);
+                            compute(tb, lb + 1);
+                            if (q2 >= qe) break;
+                            q = q2;
+                            lb += 2;
+                        }
+                    }
+                }
+
+                // ---- phase 2: exact evaluation inside each permutation's winning block ------------------------
+                uint32_t res[P];
+                unsigned need_slow = 0;
+                constexpr int G = P < 4 ? P : 4;   // permutations handled together (bounds live registers for P = 8)
+#pragma unroll
+                for (int j0 = 0; j0 < P; j0 += G) {
+                    uint4 v[G][4];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const uint4 *wb = reinterpret_cast<const uint4 *>(src + (m[j0 + g] & kKeyMask) * 16u);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[g][i] = wb[i];
+                    }
+                    uint4 w[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int j = j0 + g;
+                        const uint32_t c = c7[j];
+                        uint32_t gm[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            gm[i] = min(umin3(alo[j] * v[g][i].x + c, alo[j] * v[g][i].y + c, alo[j] * v[g][i].z + c),
+                                        alo[j] * v[g][i].w + c);
+                        const uint32_t thr = min(umin3(gm[0], gm[1], gm[2]), gm[3]) + 7u;   // a wrap implies m2 - m <= window
+                        // groups made of padding only (last block) repeat a real token: they never count as a second group
+                        const int gv = ngrp - (int)(m[j] & kKeyMask) * 4;
+                        const bool in0 = gm[0] <= thr, in1 = gm[1] <= thr && gv > 1, in2 = gm[2] <= thr && gv > 2,
+                                   in3 = gm[3] <= thr && gv > 3;
+                        const int nin = (int)in0 + (int)in1 + (int)in2 + (int)in3;
+                        // another block or another group inside the window, or L'-7 may wrap: the warp resolves it below
+                        if (nin != 1 || m[j] <= kKeyMask || (m2[j] - m[j]) <= kNearWindow) need_slow |= 1u << j;
+                        w[g] = in0 ? v[g][0] : in1 ? v[g][1] : in2 ? v[g][2] : v[g][3];
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int j = j0 + g;
+                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | (c7[j] - 7u);
+                        res[j] = min(umin3(sig_eval(alo[j], ahi[j], b64, w[g].x), sig_eval(alo[j], ahi[j], b64, w[g].y),
+                                           sig_eval(alo[j], ahi[j], b64, w[g].z)), sig_eval(alo[j], ahi[j], b64, w[g].w));
+                    }
+                }
+
+                // ---- flagged permutations: exact evaluation of the whole sub-piece, spread over the lanes ------------
+                if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
+                    int nflag = 0;
+                    const int n_pad = nblk * 16;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        unsigned bal = __ballot_sync(0xFFFFFFFFu, (need_slow >> j) & 1u);
+                        nflag += __popc(bal);
+                        while (bal) {
+                            const int owner = __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            const uint32_t fa_lo = __shfl_sync(0xFFFFFFFFu, alo[j], owner);
+                            const uint32_t fa_hi = __shfl_sync(0xFFFFFFFFu, ahi[j], owner);
+                            const uint32_t fb_lo = __shfl_sync(0xFFFFFFFFu, c7[j], owner) - 7u;
+                            const uint32_t fb_hi = __shfl_sync(0xFFFFFFFFu, bhi[j], owner);
+                            const uint64_t b64 = ((uint64_t)fb_hi << 32) | fb_lo;
+                            uint32_t r = 0xFFFFFFFFu;
+                            for (int i = lane; i < n_pad; i += 32) r = min(r, sig_eval(fa_lo, fa_hi, b64, src[i]));
+                            r = __reduce_min_sync(0xFFFFFFFFu, r);
+                            if (lane == owner) res[j] = r;
+                        }
+                    }
+                    DSK_SIG_STAT(STAT_FLAGGED, nflag);
+                    // repeated tokens tie across blocks: from now on this warp deduplicates while it stages
+                    if (nflag >= 4 && !dedupe) { dedupe = true; clean_run = 0; }
+                }
+#pragma unroll
+                for (int j = 0; j < P; ++j) acc[j] = min(acc[j], res[j]);
+            }
+
+            // ---- merge with the running state (minhash.py:297) and store ---------------------------
+            if (prm.init != nullptr) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    if (kl + j < K) {
+                        const int64_t e = d * prm.init_stride + kl + j;
+                        if (prm.init_is_u64) {
+                            const uint64_t v = __ldg(static_cast<const uint64_t *>(prm.init) + e);
+                            acc[j] = (uint32_t)min((uint64_t)acc[j], v);  // acc <= 2^32-1 so the min fits
+                        } else {
+                            acc[j] = min(acc[j], __ldg(static_cast<const uint32_t *>(prm.init) + e));
+                        }
+                    }
+                }
+            }
+            // One store per destination: the caller's matrix, or -- fused all-gather -- the same row of the full
+            // [N_total, K] matrix on EVERY rank (peer pointers mapped over NVLink; plain st.global to a peer address).
+            const int n_dst = prm.n_peers > 0 ? prm.n_peers : 1;
+            for (int pd = 0; pd < n_dst; ++pd) {
+                void *obase = prm.n_peers > 0 ? prm.peer_out[pd] : prm.out;
+                const int64_t orow = d + (prm.n_peers > 0 ? prm.peer_row_offset : 0);
+                if (prm.out_is_u64) {
+                    uint64_t *row = static_cast<uint64_t *>(obase) + orow * (int64_t)K + kl;
+#pragma unroll
+                    for (int j = 0; j < P; ++j)
+                        if (kl + j < K) row[j] = acc[j];
+                } else {
+                    uint32_t *row = static_cast<uint32_t *>(obase) + orow * (int64_t)K + kl;
+                    if (P == 4 && (K & 3) == 0) {
+                        if (kl < K) *reinterpret_cast<uint4 *>(row) = make_uint4(acc[0], acc[1 % P], acc[2 % P], acc[3 % P]);
+                    } else if (P == 8 && (K & 7) == 0) {
+                        if (kl < K) {
+                            reinterpret_cast<uint4 *>(row)[0] = make_uint4(acc[0], acc[1 % P], acc[2 % P], acc[3 % P]);
+                            reinterpret_cast<uint4 *>(row)[1] = make_uint4(acc[4 % P], acc[5 % P], acc[6 % P], acc[7 % P]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < P; ++j)
+                            if (kl + j < K) row[j] = acc[j];
+                    }
+                }
+            }
+            start = end;
+        }
+    }  // units
+}
+
+template <int P, int OCC>
+static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
+    BulkParams prm = prm_in;
+    const int slices = (prm.k + 32 * P - 1) / (32 * P);
+    int64_t gx = (prm.n_docs + kSigWarps - 1) / kSigWarps;
+    int64_t gmax = (int64_t)sm_count * OCC / slices;  // persistent: every CTA of every slice resident, one wave
+    if (gmax < 1) gmax = 1;
+    if (gx > gmax) gx = gmax;
+    if (gx < 1) gx = 1;
+    // unit size: ~8 units per warp for balance, at most 32 documents so a unit's ring restart is amortised
+    if (prm.docs_per_unit <= 0) {   // 0 = choose here; > 0 = forced by the caller (tests)
+        int64_t dpu = prm.n_docs / (gx * kSigWarps * 8);
+        prm.docs_per_unit = (int)(dpu < 1 ? 1 : (dpu > 32 ? 32 : dpu));
+    }
+    cudaError_t e = cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned) * (size_t)slices, s);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)gx, (unsigned)slices);
+    DSK_LAUNCH((minhash_sig_kernel<P, OCC>), grid, kSigWarps * 32, 0, s, prm);
+    return cudaGetLastError();
+}
+
+// CTAs per SM the kernel is compiled for (register cap = 65536 / (128 * OCC)); DSK_SIG_OCC = 4 | 5 for experiments
+static int sig_occ() {
+    static int occ = [] {
+        const char *e = getenv("DSK_SIG_OCC");
+        const int v = e ? atoi(e) : 4;
+        return (v == 4 || v == 5) ? v : 4;
+    }();
+    return occ;
+}
+
+cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s) {
+    if (prm.k <= 32) return launch_sig<1, 4>(prm, sm_count, s);
+    if (prm.k <= 64) return launch_sig<2, 4>(prm, sm_count, s);
+    if (prm.k <= 128) return sig_occ() == 5 ? launch_sig<4, 5>(prm, sm_count, s) : launch_sig<4, 4>(prm, sm_count, s);
+    return launch_sig<8, 4>(prm, sm_count, s);
+}
+
+}  // namespace dsk

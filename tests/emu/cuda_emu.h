@@ -72,6 +72,10 @@ static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long 
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
     return cmp;
 }
+static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val) {
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return cmp;
+}
 static inline int atomicCAS(int *p, int cmp, int val) {
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
     return cmp;
@@ -181,6 +185,17 @@ static inline unsigned emu_ballot(bool pred) {
     pthread_barrier_wait(&emu_warp->bar);
     unsigned m = 0;
     for (int i = 0; i < 32; ++i) m |= (unsigned)emu_warp->slot[i] << i;
+    pthread_barrier_wait(&emu_warp->bar);
+    return m;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) { return emu_ballot(pred != 0); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {   // redux.sync.min.u32
+    emu_warp->slot[emu_lane] = v;
+    pthread_barrier_wait(&emu_warp->bar);
+    unsigned m = 0xFFFFFFFFu;
+    for (int i = 0; i < 32; ++i) m = emu_warp->slot[i] < m ? (unsigned)emu_warp->slot[i] : m;
     pthread_barrier_wait(&emu_warp->bar);
     return m;
 }

@@ -13,6 +13,7 @@ thread_local int emu_lane = 0;
 thread_local EmuCta *emu_cta = nullptr;
 
 #include "../../datasketch_b200/csrc/minhash_kernels.cu"
+#include "../../datasketch_b200/csrc/signature_kernel.cu"
 #include "../../datasketch_b200/csrc/codec_kernels.cu"
 #include "../../datasketch_b200/csrc/lsh_kernels.cu"
 #include "../../datasketch_b200/csrc/jaccard_kernels.cu"

@@ -9,6 +9,7 @@ thread_local int emu_lane = 0;
 thread_local EmuCta *emu_cta = nullptr;
 
 #include "../../datasketch_b200/csrc/minhash_kernels.cu"
+#include "../../datasketch_b200/csrc/signature_kernel.cu"
 #include "../../datasketch_b200/csrc/codec_kernels.cu"
 #include "../../datasketch_b200/csrc/lsh_kernels.cu"
 #include "../../datasketch_b200/csrc/jaccard_kernels.cu"
@@ -19,36 +20,44 @@ thread_local EmuCta *emu_cta = nullptr;
 #include <vector>
 
 // a / b: the uint64 permutation parameters; init (optional): [n_docs or 1][k] u32/u64 running signatures.
-// rescan = 0 goes through the product launcher (launch_minhash_bulk: P selection, slices, unit size, counters);
-// rescan = 1 instantiates the opt-in re-scan variant directly (the launcher reads DSK_RESCAN once per process).
+// Goes through the product launcher (launch_minhash_bulk: kernel and P selection, slices, counters); docs_per_unit > 0
+// forces the unit size, grid_x plays the role of sm_count (the launcher's grid is grid_x * OCC CTAs at most).
+// v1 = 1 runs the round-1 two-phase kernel (minhash_bulk_kernel<MODE_TWO_PHASE>) instead of minhash_sig_kernel.
 extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
-                                const uint64_t *a, const uint64_t *b, int k, int mode, int rescan,
+                                const uint64_t *a, const uint64_t *b, int k, int mode, int v1,
                                 const void *init, int64_t init_stride, int init_is_u64, void *out, int out_is_u64,
                                 int docs_per_unit, int grid_x) {
     const int P = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 8;
-    const int slices = (k + 32 * P - 1) / (32 * P);
     const int kpad = (k + 255) / 256 * 256;
-    std::vector<uint32_t> tab((size_t)4 * kpad);
+    std::vector<uint32_t> tab((size_t)5 * kpad);
     for (int i = 0; i < kpad; ++i) {  // padding slots repeat real permutations, like dsk_perm_create
         const int s = i % k;
         tab[i] = (uint32_t)a[s]; tab[kpad + i] = (uint32_t)(a[s] >> 32);
         tab[2 * kpad + i] = (uint32_t)b[s]; tab[3 * kpad + i] = (uint32_t)(b[s] >> 32);
+        tab[4 * kpad + i] = (uint32_t)b[s] + 7u;
     }
     std::vector<unsigned> counters(64, 0u);
     dsk::BulkParams prm{};
     prm.tokens = tokens; prm.offsets = offsets; prm.n_docs = n_docs; prm.n_tokens = offsets[n_docs];
-    prm.a_lo = tab.data(); prm.a_hi = tab.data() + kpad; prm.b_lo = tab.data() + 2 * kpad; prm.b_hi = tab.data() + 3 * kpad;
+    prm.a_lo = tab.data(); prm.a_hi = tab.data() + kpad; prm.b_lo = tab.data() + 2 * kpad; prm.b_hi = tab.data() + 3 * kpad; prm.b_lo7 = tab.data() + 4 * kpad;
     prm.k = k; prm.init = init; prm.init_stride = init_stride; prm.init_is_u64 = init_is_u64;
     prm.out = out; prm.out_is_u64 = out_is_u64; prm.work_counter = counters.data();
     prm.docs_per_unit = docs_per_unit; prm.n_peers = 0; prm.peer_row_offset = 0;
     if (token_is_u64 && mode != dsk::MODE_EXACT) return -1;
-    if (!rescan || P < 4)   // (the variant exists for P = 4 and 8 only)  sm_count = grid_x / 4 CTAs per SM -> the launcher's grid is grid_x (per slice) for small inputs
-        return dsk::launch_minhash_bulk(prm, mode, token_is_u64, grid_x, nullptr);
-    if (mode != dsk::MODE_TWO_PHASE) return -1;
-    dim3 grid((unsigned)grid_x, (unsigned)slices);
-    if (P == 4) emu_launch(dsk::minhash_bulk_kernel<4, dsk::MODE_TWO_PHASE, uint32_t, 4, 1>, grid, dsk::kWarps * 32, 0, prm);
-    else emu_launch(dsk::minhash_bulk_kernel<8, dsk::MODE_TWO_PHASE, uint32_t, 4, 1>, grid, dsk::kWarps * 32, 0, prm);
-    return 0;
+    if (v1 && mode == dsk::MODE_TWO_PHASE) {
+        switch (P) {
+            case 1: return dsk::launch_bulk<1, dsk::MODE_TWO_PHASE, uint32_t, 4>(prm, grid_x, nullptr);
+            case 2: return dsk::launch_bulk<2, dsk::MODE_TWO_PHASE, uint32_t, 4>(prm, grid_x, nullptr);
+            case 4: return dsk::launch_bulk<4, dsk::MODE_TWO_PHASE, uint32_t, 4>(prm, grid_x, nullptr);
+            default: return dsk::launch_bulk<8, dsk::MODE_TWO_PHASE, uint32_t, 4>(prm, grid_x, nullptr);
+        }
+    }
+    return dsk::launch_minhash_bulk(prm, mode, token_is_u64, grid_x, nullptr);
+}
+
+// path counters of minhash_sig_kernel (read-and-reset): in place / copied / deduplicated sub-pieces, tokens removed, flagged perms
+extern "C" void emu_sig_stats(long long *out5) {
+    for (int i = 0; i < dsk::STAT_COUNT; ++i) out5[i] = dsk::g_sig_stat[i].exchange(0);
 }
 
 extern "C" int emu_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,

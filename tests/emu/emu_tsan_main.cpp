@@ -21,7 +21,7 @@ extern "C" int emu_lsh_insert(void *h, const uint32_t *sig, int64_t n, int sm_co
 extern "C" int64_t emu_lsh_query_count(void *h, const uint32_t *q, int64_t nq, int64_t *ptr, int sm_count);
 extern "C" int emu_lsh_query_fill(void *h, const uint32_t *q, int64_t nq, const int64_t *ptr, int32_t *idx, int sm_count);
 extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
-                                const uint64_t *a, const uint64_t *b, int k, int mode, int rescan, const void *init,
+                                const uint64_t *a, const uint64_t *b, int k, int mode, int v1, const void *init,
                                 int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int docs_per_unit,
                                 int grid_x);
 
@@ -56,12 +56,12 @@ int main() {
             }
     int bad = 0;
     for (int mode = 0; mode < 3; ++mode)
-        for (int rescan = 0; rescan < (mode == 0 ? 2 : 1); ++rescan) {
+        for (int v1 = 0; v1 < (mode == 0 ? 2 : 1); ++v1) {
             std::vector<uint32_t> got((size_t)n_docs * k, 0);
-            emu_minhash_bulk(tok.data(), 0, off.data(), n_docs, a.data(), b.data(), k, mode, rescan, nullptr, 0, 0,
+            emu_minhash_bulk(tok.data(), 0, off.data(), n_docs, a.data(), b.data(), k, mode, v1, nullptr, 0, 0,
                              got.data(), 0, 3, 2);
             const bool ok = got == want;
-            printf("mode %d rescan %d: %s\n", mode, rescan, ok ? "identical" : "MISMATCH");
+            printf("mode %d v1 %d: %s\n", mode, v1, ok ? "identical" : "MISMATCH");
             bad += !ok;
         }
     {   // LeanMinHash codec: 4-stage bulk-copy tile pipeline, several tiles per CTA, ragged last tile

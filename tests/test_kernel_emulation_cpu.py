@@ -1,11 +1,11 @@
 """The CUDA signature kernel's own source, run on the CPU against the oracle.
 
-``tests/emu/`` compiles ``datasketch_b200/csrc/minhash_kernels.cu`` and ``codec_kernels.cu`` -- kernels AND launchers --
+``tests/emu/`` compiles ``datasketch_b200/csrc/signature_kernel.cu``, ``minhash_kernels.cu`` and ``codec_kernels.cu`` -- kernels AND launchers --
 with g++ (``-DDSK_EMU``): every CUDA thread is a host thread, warp / CTA barriers are pthread barriers, and the async
 bulk copies are emulated adversarially (destination poisoned at issue, data delivered only when a waiter polls the
 mbarrier, shared->global stores deferred until ``bulk_wait_read``).  What this checks is the *logic* -- the per-warp
 ring protocol, block patching at document boundaries, the array's <16-byte tail, dynamic work units, the two-phase
-tracking with both re-scan variants, init merging, K slicing, the launchers' choices, the 4-stage TMA tile pipeline of
+tracking, the warp-wide exact path for flagged permutations and the de-duplicating stage, init merging, K slicing, the launchers' choices, the 4-stage TMA tile pipeline of
 the LeanMinHash codec -- on the exact source that nvcc compiles for the B200 (the hooks are preprocessor-only; the
 product's SASS is byte-identical with and without them).  It says nothing about performance, and the GPU tests remain
 the parity gate for the compiled kernels.
@@ -35,6 +35,7 @@ def emu():
     so = os.path.join(out, "libemu_kernels.so")
     srcs = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_emu.h"),
             os.path.join(ROOT, "datasketch_b200", "csrc", "minhash_kernels.cu"),
+            os.path.join(ROOT, "datasketch_b200", "csrc", "signature_kernel.cu"),
             os.path.join(ROOT, "datasketch_b200", "csrc", "dsk_common.cuh")] + [
                 os.path.join(ROOT, "datasketch_b200", "csrc", f + "_kernels.cu") for f in ("codec", "lsh", "jaccard", "sha1", "hash", "wmh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
@@ -45,7 +46,7 @@ def emu():
     lib.emu_minhash_bulk.argtypes = [vp, ci, vp, i64, vp, vp, ci, ci, ci, vp, i64, ci, vp, ci, ci, ci]
     lib.emu_minhash_bulk.restype = ci
 
-    def run(tok, off, perms, mode, rescan=0, init=None, out_u64=False, docs_per_unit=3, grid_x=1):
+    def run(tok, off, perms, mode, v1=0, init=None, out_u64=False, docs_per_unit=3, grid_x=1):
         k, n = perms.shape[1], len(off) - 1
         tok = np.ascontiguousarray(tok)
         off = np.ascontiguousarray(off, dtype=np.int64)
@@ -56,11 +57,16 @@ def emu():
             init = np.ascontiguousarray(init)
             ip, stride, i64f = init.ctypes.data, (0 if init.ndim == 1 else k), int(init.dtype == np.uint64)
         rc = lib.emu_minhash_bulk(tok.ctypes.data, int(tok.dtype == np.uint64), off.ctypes.data, n, a.ctypes.data,
-                                  b.ctypes.data, k, mode, rescan, ip, stride, i64f, out.ctypes.data, int(out_u64),
+                                  b.ctypes.data, k, mode, v1, ip, stride, i64f, out.ctypes.data, int(out_u64),
                                   docs_per_unit, grid_x)
         assert rc == 0
         return out
+    def stats():
+        buf = (ctypes.c_longlong * 5)()
+        lib.emu_sig_stats(buf)
+        return dict(zip(("in_place", "copied", "deduped", "removed", "flagged"), list(buf)))
     run.lib = lib
+    run.stats = stats
     return run
 
 
@@ -83,13 +89,13 @@ def test_all_modes_ragged_documents(emu, k):
     want = oc.minhash_bulk_u32tok(tok, off, perms)
     for mode in (TWO_PHASE, DIRECT, EXACT):
         assert np.array_equal(emu(tok, off, perms, mode), want), (k, mode)
-    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=1), want)
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, v1=1), want)
 
 
-@pytest.mark.parametrize("rescan", [0, 1])
+@pytest.mark.parametrize("v1", [0, 1])
 @pytest.mark.parametrize("share", [0.05, 0.6])
-def test_repeated_tokens_take_the_rescan_and_stay_exact(emu, rescan, share):
-    rs = np.random.RandomState(int(share * 100) + rescan)
+def test_repeated_tokens_stay_exact(emu, v1, share):
+    rs = np.random.RandomState(int(share * 100) + v1)
     tok, off = _ragged(rs, 50, 400, extra_tail=1)
     for d in range(len(off) - 1):
         a, b = int(off[d]), int(off[d + 1])
@@ -99,18 +105,18 @@ def test_repeated_tokens_take_the_rescan_and_stay_exact(emu, rescan, share):
             tok[a + rep] = tok[a + (rs.uniform(size=len(rep)) * rep).astype(np.int64)]
     for k in (128, 256):
         perms = o.init_permutations(k, 2)
-        assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=rescan), oc.minhash_bulk_u32tok(tok, off, perms))
+        assert np.array_equal(emu(tok, off, perms, TWO_PHASE, v1=v1), oc.minhash_bulk_u32tok(tok, off, perms))
 
 
-@pytest.mark.parametrize("rescan", [0, 1])
-def test_structured_tokens_small_minimum_and_wrap(emu, rescan):
+@pytest.mark.parametrize("v1", [0, 1])
+def test_structured_tokens_small_minimum_and_wrap(emu, v1):
     """Tiny and near-2^32 tokens: products next to the wrap, min L' < 7 cases, many exact ties."""
     tok = np.concatenate([np.arange(0, 3000, dtype=np.uint32),
                           (np.uint64(1 << 32) - np.arange(1, 3001, dtype=np.uint64)).astype(np.uint32),
                           np.zeros(500, dtype=np.uint32), np.full(500, 0xFFFFFFFF, dtype=np.uint32)])
     off = np.arange(0, len(tok) + 1, 125, dtype=np.int64)
     perms = o.init_permutations(128, 3)
-    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=rescan), oc.minhash_bulk_u32tok(tok, off, perms))
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, v1=v1), oc.minhash_bulk_u32tok(tok, off, perms))
 
 
 def test_long_documents_leave_the_ring_and_units_of_every_size(emu):
@@ -123,9 +129,62 @@ def test_long_documents_leave_the_ring_and_units_of_every_size(emu):
     perms = o.init_permutations(128, 1)
     want = oc.minhash_bulk_u32tok(tok, off, perms)
     for dpu, gx in ((1, 2), (5, 1), (32, 2)):
-        for rescan in (0, 1):
-            assert np.array_equal(emu(tok, off, perms, TWO_PHASE, rescan=rescan, docs_per_unit=dpu, grid_x=gx), want)
+        for v1 in (0, 1):
+            assert np.array_equal(emu(tok, off, perms, TWO_PHASE, v1=v1, docs_per_unit=dpu, grid_x=gx), want)
     assert np.array_equal(emu(tok, off, perms, DIRECT, docs_per_unit=2, grid_x=2), want)
+
+
+@pytest.mark.parametrize("T", [16, 64, 256, 512, 528, 1040])
+def test_aligned_documents_use_the_ring_in_place(emu, T):
+    """Documents whose length is a multiple of 16 and whose start is 16-byte aligned are read straight from the ring
+    (signature_kernel.cu "in place"); the ones that would wrap the 1024-token ring, and every sub-piece after an odd
+    one, take the copy.  A 4-token shift of the whole batch changes which documents wrap."""
+    rs = np.random.RandomState(T)
+    n = 37
+    for lead in (0, 4, 20):                     # one leading document of `lead` tokens shifts everything behind it
+        lens = np.full(n, T, dtype=np.int64)
+        lens[0] = lead
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+        for k in (128, 256):
+            perms = o.init_permutations(k, 1)
+            want = oc.minhash_bulk_u32tok(tok, off, perms)
+            for dpu, gx in ((32, 1), (5, 2)):
+                emu.stats()
+                assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=dpu, grid_x=gx), want), (T, lead, k, dpu)
+                st = emu.stats()
+                assert st["in_place"] > 0 and st["deduped"] == 0, st
+                if lead == 0 and T in (16, 64, 256, 512):      # nothing wraps, nothing is ragged: never copied
+                    assert st["copied"] == 0, st
+                if T == 1040 or lead == 20:
+                    assert st["copied"] > 0, st
+
+
+def test_deduplication_switches_on_and_off(emu):
+    """Repeated tokens tie across blocks; after a sub-piece with >= 4 flagged permutations the warp deduplicates while
+    it stages, and stops again after 16 sub-pieces in which nothing was removed.  One warp (grid 1 x 1 CTA, one
+    unit) walks: clean -> heavy repeats -> clean (long enough to switch off) -> repeats again; 0xFFFFFFFF tokens
+    (the hash set's empty marker) are repeated too."""
+    rs = np.random.RandomState(77)
+    lens = [256] * 4 + [300] * 6 + [256] * 40 + [190] * 4 + [1200, 256]
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    for d in list(range(4, 10)) + list(range(50, 55)):
+        a, b = int(off[d]), int(off[d + 1])
+        pool = tok[a:a + max(8, (b - a) // 3)].copy()
+        pool[0] = 0xFFFFFFFF
+        tok[a:b] = pool[rs.randint(0, len(pool), size=b - a)]
+    perms = o.init_permutations(128, 9)
+    want = oc.minhash_bulk_u32tok(tok, off, perms)
+    emu.stats()
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=64, grid_x=1), want)
+    st = emu.stats()
+    # one warp walked everything: it staged in place first, flagged the repeats, de-duplicated (removing tokens),
+    # went back to in-place staging during the 40 clean documents and de-duplicated again at the end
+    assert st["flagged"] >= 8 and st["removed"] > 500 and 16 <= st["deduped"] < 45 and st["in_place"] >= 20, st
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=7, grid_x=2), want)
 
 
 def test_u64_tokens_init_merge_and_u64_output(emu):
@@ -432,7 +491,7 @@ def _fuzz_signature_kernel(run, seed, iterations):
                 tok[:T // 2] = rs.randint(0, 20, size=T // 2)
             mode = int(rs.randint(0, 3))
         perms = o.init_permutations(k, int(rs.randint(1, 50)))
-        rescan = int(rs.randint(0, 2)) if mode == TWO_PHASE else 0
+        v1 = int(rs.randint(0, 2)) if mode == TWO_PHASE else 0
         init, u = None, rs.uniform()
         if u < 0.2:
             init = rs.randint(0, 1 << 32, size=k, dtype=np.uint64)
@@ -443,10 +502,10 @@ def _fuzz_signature_kernel(run, seed, iterations):
         want = (oc.minhash_bulk_u64tok(tok, off, perms) if is64 else oc.minhash_bulk_u32tok(tok, off, perms)).astype(np.uint64)
         if init is not None:
             want = np.minimum(want, init.astype(np.uint64) if init.ndim == 2 else init.astype(np.uint64)[None, :])
-        got = run(tok, off, perms, mode, rescan=rescan, init=init, out_u64=bool(rs.randint(0, 2)),
+        got = run(tok, off, perms, mode, v1=v1, init=init, out_u64=bool(rs.randint(0, 2)),
                   docs_per_unit=int(rs.choice([1, 2, 3, 7, 32])), grid_x=int(rs.randint(1, 3)))
         assert np.array_equal(got.astype(np.uint64), want), dict(seed=seed, it=it, k=k, n=n, style=style, is64=bool(is64),
-                                                                 mode=mode, rescan=rescan, tokens=T)
+                                                                 mode=mode, v1=v1, tokens=T)
     return iterations
 
 
