@@ -65,6 +65,11 @@ SIGNATURES = {
     "dsk_lean_unpack": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dsk_band_keys": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsk_band_fingerprints": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsk_band_sums": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsk_bloom_insert": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_int,
+                                 c_void_p]),
+    "dsk_bloom_query": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_int,
+                                c_void_p, c_void_p]),
 }
 
 _lib = None

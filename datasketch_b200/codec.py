@@ -108,6 +108,20 @@ def band_fingerprints(sig, b: int, r: int, stream=None):
     return out
 
 
+def band_sums(sig, b: int, r: int, stream=None):
+    """[N, K] u32 signatures -> [N, b] int64 tensor holding the uint64 Bloom keys of MinHashLSHBloom:
+    ``sum(hashvalues[j*r:(j+1)*r]) % (2**61 - 1)`` per band (datasketch/lsh_bloom.py:105, :116)."""
+    torch = _torch()
+    d_sig, is64 = _as_device_sig(sig)
+    if is64:
+        raise TypeError("band_sums takes the 32-bit signature matrix")
+    n, k = d_sig.shape
+    out = torch.empty((n, b), dtype=torch.int64, device=d_sig.device)
+    with torch.cuda.device(d_sig.device):
+        nv.check(nv.load().dsk_band_sums(d_sig.data_ptr(), n, k, b, r, out.data_ptr(), _stream(d_sig, stream)))
+    return out
+
+
 def jaccard_pairs(sig, i, j, stream=None):
     """Jaccard estimates of the row pairs (i[p], j[p]) of one signature matrix: float64 array of
     ``count_equal / K`` exactly as ``MinHash.jaccard`` (minhash.py:324) computes it."""

@@ -446,6 +446,65 @@ int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm, int b,
     return DSK_OK;
 }
 
+int dsk_band_sums(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint64_t *d_keys, void *stream) {
+    int rc = check_bands("dsk_band_sums", n, num_perm, b, r);
+    if (rc) return rc;
+    if (n > 0 && (!d_sig || !d_keys)) {
+        set_error("dsk_band_sums: null buffer");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_band_sums(d_sig, n, num_perm, b, r, d_keys, dev->sm_count, (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+static int check_bloom(const char *who, const void *d_bits, uint64_t words_per_table, uint64_t n_bits, int n_hashes) {
+    if (!d_bits || n_bits == 0 || n_hashes <= 0 || n_hashes > 64 || words_per_table * 32 < n_bits ||
+        ((uintptr_t)d_bits & 3) != 0) {
+        set_error("%s: need a 4-byte aligned bit array, 0 < n_hashes <= 64 and words_per_table * 32 >= n_bits > 0", who);
+        return DSK_ERR_INVALID;
+    }
+    return DSK_OK;
+}
+
+int dsk_bloom_insert(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint32_t *d_bits,
+                     uint64_t words_per_table, uint64_t n_bits, int n_hashes, void *stream) {
+    int rc = check_bands("dsk_bloom_insert", n, num_perm, b, r);
+    if (rc) return rc;
+    rc = check_bloom("dsk_bloom_insert", d_bits, words_per_table, n_bits, n_hashes);
+    if (rc) return rc;
+    if (n > 0 && !d_sig) {
+        set_error("dsk_bloom_insert: null signature matrix");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_bloom_insert(d_sig, n, num_perm, b, r, d_bits, words_per_table, n_bits, n_hashes, dev->sm_count,
+                                 (cudaStream_t)stream));
+    return DSK_OK;
+}
+
+int dsk_bloom_query(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, const uint32_t *d_bits,
+                    uint64_t words_per_table, uint64_t n_bits, int n_hashes, uint8_t *d_hit, void *stream) {
+    int rc = check_bands("dsk_bloom_query", n, num_perm, b, r);
+    if (rc) return rc;
+    rc = check_bloom("dsk_bloom_query", d_bits, words_per_table, n_bits, n_hashes);
+    if (rc) return rc;
+    if (n > 0 && (!d_sig || !d_hit)) {
+        set_error("dsk_bloom_query: null buffer");
+        return DSK_ERR_INVALID;
+    }
+    DevInfo *dev;
+    rc = current_dev(&dev);
+    if (rc) return rc;
+    DSK_CUDA(launch_bloom_query(d_sig, n, num_perm, b, r, d_bits, words_per_table, n_bits, n_hashes, d_hit, dev->sm_count,
+                                (cudaStream_t)stream));
+    return DSK_OK;
+}
+
 int dsk_wmh_create(const float *h_rs, const float *h_ln_cs, const float *h_betas, int sample_size, int dim, int device,
                    dsk_wmh **out) {
     if (!h_rs || !h_ln_cs || !h_betas || !out || sample_size <= 0 || dim <= 0) {

@@ -75,6 +75,13 @@ cudaError_t launch_band_keys_be(const uint32_t *sig, int64_t n, int k, int b, in
 cudaError_t launch_band_fingerprints(const uint32_t *sig, int64_t n, int k, int b, int r, uint64_t *out, int sm_count,
                                      cudaStream_t s);
 
+cudaError_t launch_band_sums(const uint32_t *sig, int64_t n, int k, int b, int r, uint64_t *keys, int sm_count, cudaStream_t s);
+cudaError_t launch_bloom_insert(const uint32_t *sig, int64_t n, int k, int b, int r, uint32_t *bits, uint64_t words_per_table,
+                                uint64_t n_bits, int n_hashes, int sm_count, cudaStream_t s);
+cudaError_t launch_bloom_query(const uint32_t *sig, int64_t n, int k, int b, int r, const uint32_t *bits,
+                               uint64_t words_per_table, uint64_t n_bits, int n_hashes, uint8_t *hit, int sm_count,
+                               cudaStream_t s);
+
 cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, float *dst, cudaStream_t s);
 cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *betas_t, int ss, int ss_pad, int dim,
                        const float *v, int64_t n, int64_t *out, int32_t *status, int many, int sm_count,

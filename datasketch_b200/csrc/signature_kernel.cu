@@ -21,9 +21,11 @@
 //   phase 2  per permutation: recompute L' on the winning block (block index = m & 31), find the one 4-token group
 //            inside the +7 window and evaluate those 4 tokens exactly (groups that hold padding only are ignored).
 //   flagged  a permutation with another block inside the window (m2 - m <= 69), a second group inside the window,
-//            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp: every lane
-//            evaluates r exactly for 1/32 of the sub-piece's tokens under that permutation, then one
-//            redux.sync.min.  Exact for any input; costs ~50 issue slots per flagged (document, permutation).
+//            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp, two permutations
+//            at a time: every lane filters 1/32 of the sub-piece's tokens with L' and evaluates r exactly for the
+//            ones inside the window, then one redux.sync.min.  Exact for any input; ~40 issue slots per flagged
+//            (document, permutation).  A sub-piece with >= 24 flagged permutations (heavy repetition) switches the
+//            warp to de-duplicating staging, which removes the ties at their source.
 #include "dsk_common.cuh"
 
 namespace dsk {
@@ -38,6 +40,7 @@ constexpr int kTabSlots = 1024;     // dedupe hash set (load factor <= 0.5)
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kKeyMask = 31u;  // low bits of a tracking key hold the block index (32 blocks of 16 tokens)
 constexpr uint32_t kNearWindow = 7u + 2u * kKeyMask;  // m2 - m <= this: another block may be inside the +7 window
+constexpr int kDedupeOnFlags = 24;  // flagged permutations in one sub-piece (of 32*P) that switch de-duplication on
 
 // Path counters for the CPU emulation tests (tests/emu): which staging path / how many flagged permutations.
 // The product build compiles them away.
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                 }
 
                 // ---- phase 2: exact evaluation inside each permutation's winning block ------------------------
-                uint32_t res[P];
+                uint32_t res[P], win[P];   // win: upper end of the L' window the flagged path must evaluate
                 unsigned need_slow = 0;
                 constexpr int G = P < 4 ? P : 4;   // permutations handled together (bounds live registers for P = 8)
 #pragma unroll
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[g][i] = wb[i];
                     }
-                    uint4 w[G];
+                    const uint4 *wsrc[G];   // the one group inside the window (re-read below: 5 ops instead of 12 selects)
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const int j = j0 + g;
@@ -310,8 +313,12 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         const int nin = (int)in0 + (int)in1 + (int)in2 + (int)in3;
                         // another block or another group inside the window, or L'-7 may wrap: the warp resolves it below
                         if (nin != 1 || m[j] <= kKeyMask || (m2[j] - m[j]) <= kNearWindow) need_slow |= 1u << j;
-                        w[g] = in0 ? v[g][0] : in1 ? v[g][1] : in2 ? v[g][2] : v[g][3];
+                        win[j] = (m[j] <= kKeyMask || thr < 7u) ? 0xFFFFFFFFu : thr;
+                        wsrc[g] = reinterpret_cast<const uint4 *>(src + (m[j] & kKeyMask) * 16u) + (in0 ? 0 : in1 ? 1 : in2 ? 2 : 3);
                     }
+                    uint4 w[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) w[g] = *wsrc[g];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const int j = j0 + g;
@@ -321,7 +328,10 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                     }
                 }
 
-                // ---- flagged permutations: exact evaluation of the whole sub-piece, spread over the lanes ------------
+                // ---- flagged permutations: resolved by the whole warp, two at a time ---------------------------------
+                // Every lane filters 1/32 of the sub-piece's tokens with the one-IMAD value L' and evaluates exactly the
+                // ones inside the window [.., win]: a token with L' > (winning block's min L') + 7 cannot hold the
+                // minimum (r >= L' - 7).  win = 2^32-1 (evaluate everything) when L' - 7 may wrap.
                 if (__any_sync(0xFFFFFFFFu, need_slow != 0)) {
                     int nflag = 0;
                     const int n_pad = nblk * 16;
@@ -330,22 +340,35 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         unsigned bal = __ballot_sync(0xFFFFFFFFu, (need_slow >> j) & 1u);
                         nflag += __popc(bal);
                         while (bal) {
-                            const int owner = __ffs(bal) - 1;
+                            const int o0 = __ffs(bal) - 1;
                             bal &= bal - 1;
-                            const uint32_t fa_lo = __shfl_sync(0xFFFFFFFFu, alo[j], owner);
-                            const uint32_t fa_hi = __shfl_sync(0xFFFFFFFFu, ahi[j], owner);
-                            const uint32_t fb_lo = __shfl_sync(0xFFFFFFFFu, c7[j], owner) - 7u;
-                            const uint32_t fb_hi = __shfl_sync(0xFFFFFFFFu, bhi[j], owner);
-                            const uint64_t b64 = ((uint64_t)fb_hi << 32) | fb_lo;
-                            uint32_t r = 0xFFFFFFFFu;
-                            for (int i = lane; i < n_pad; i += 32) r = min(r, sig_eval(fa_lo, fa_hi, b64, src[i]));
-                            r = __reduce_min_sync(0xFFFFFFFFu, r);
-                            if (lane == owner) res[j] = r;
+                            const int o1 = bal ? __ffs(bal) - 1 : o0;    // second owner (or the first one again)
+                            bal &= bal - 1;
+                            const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, alo[j], o0), a1 = __shfl_sync(0xFFFFFFFFu, alo[j], o1);
+                            const uint32_t h0 = __shfl_sync(0xFFFFFFFFu, ahi[j], o0), h1 = __shfl_sync(0xFFFFFFFFu, ahi[j], o1);
+                            const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, c7[j], o0), c1 = __shfl_sync(0xFFFFFFFFu, c7[j], o1);
+                            const uint32_t g0 = __shfl_sync(0xFFFFFFFFu, bhi[j], o0), g1 = __shfl_sync(0xFFFFFFFFu, bhi[j], o1);
+                            const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, win[j], o0), w1 = __shfl_sync(0xFFFFFFFFu, win[j], o1);
+                            const uint64_t b0 = ((uint64_t)g0 << 32) | (c0 - 7u), b1 = ((uint64_t)g1 << 32) | (c1 - 7u);
+                            uint32_t r0 = 0xFFFFFFFFu, r1 = 0xFFFFFFFFu;
+#pragma unroll 4
+                            for (int i = lane; i < n_pad; i += 32) {
+                                const uint32_t t = src[i];
+                                const bool k0 = a0 * t + c0 <= w0, k1 = a1 * t + c1 <= w1;
+                                if (k0 || k1) {
+                                    if (k0) r0 = min(r0, sig_eval(a0, h0, b0, t));
+                                    if (k1) r1 = min(r1, sig_eval(a1, h1, b1, t));
+                                }
+                            }
+                            r0 = __reduce_min_sync(0xFFFFFFFFu, r0);
+                            r1 = __reduce_min_sync(0xFFFFFFFFu, r1);
+                            if (lane == o1) res[j] = r1;
+                            if (lane == o0) res[j] = r0;
                         }
                     }
                     DSK_SIG_STAT(STAT_FLAGGED, nflag);
-                    // repeated tokens tie across blocks: from now on this warp deduplicates while it stages
-                    if (nflag >= 4 && !dedupe) { dedupe = true; clean_run = 0; }
+                    // many ties = many repeated tokens: from now on this warp deduplicates while it stages
+                    if (nflag >= kDedupeOnFlags && !dedupe) { dedupe = true; clean_run = 0; }
                 }
 #pragma unroll
                 for (int j = 0; j < P; ++j) acc[j] = min(acc[j], res[j]);

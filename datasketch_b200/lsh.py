@@ -286,6 +286,26 @@ class MinHashLSH:
         for k, Hs in zip(skeys, self._batch_band_keys(sig)):
             self._store(k, Hs)
 
+    def export_redis(self, basename: bytes, prepickle: Optional[bool] = None):
+        """This index in the reference's Redis layout (``storage_export.RedisLayout``; lsh.py:191-200,
+        storage.py:902-1049): the state ``MinHashLSH(storage_config={"type": "redis", "basename": basename})`` would
+        hold after the same inserts.  Keys are pickled unless ``prepickle=False`` (then they must be bytes)."""
+        from .storage_export import RedisLayout
+        prepickle = True if prepickle is None else prepickle
+        layout = RedisLayout(basename, self.b)
+        for key in self.keys.keys():
+            hs = list(self.keys.get(key))
+            stored = key
+            if self.prepickle:                     # this index already holds pickled keys
+                if not prepickle:
+                    stored = pickle.loads(key)
+            elif prepickle:
+                stored = pickle.dumps(key)
+            if not isinstance(stored, bytes):
+                raise TypeError("prepickle=False requires bytes keys for non-dict storage, got %s" % type(stored).__name__)
+            layout.add(stored, hs)
+        return layout
+
     # -- merge (lsh.py:233-251, :349-368) -------------------------------------------------------------------------
     def merge(self, other: "MinHashLSH", check_overlap: bool = False):
         self._merge(other, check_overlap=check_overlap, buffer=False)

@@ -141,6 +141,22 @@ DSK_API int dsk_band_keys(const uint32_t *d_sig, int64_t n, int num_perm, int b,
 DSK_API int dsk_band_fingerprints(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint64_t *d_fp,
                                   void *stream);
 
+/* ---- MinHashLSHBloom ("next" row) -----------------------------------------------
+ * dsk_band_sums: the Bloom key of every band, d_keys[i][j] = sum(sig[i][j*r:(j+1)*r]) % (2^61 - 1) as uint64
+ * ([n, b]) -- BloomTable.insert / query's `x = sum(hashvalues) % _mersenne_prime`
+ * (datasketch/lsh_bloom.py:94-106, :108-118, :20).  HBM-bound codec: 4*num_perm bytes in, 8*b out per document.
+ * dsk_bloom_insert / dsk_bloom_query: the same keys go straight into / are tested against b device-resident
+ * Bloom tables (MinHashLSHBloom._insert :308-316, query :365-371: a hit in ANY band flags the document).
+ * d_bits is [b][words_per_table] uint32, caller-owned and zero-initialised; each key sets / tests n_hashes
+ * bits among the table's first n_bits bits (double hashing).  The reference delegates the bit tables to
+ * pybloomfilter; these are the library's own (no false negatives, the usual (1 - e^(-kn/m))^k false-positive
+ * rate), not pybloomfilter's file format.  d_hit is [n] uint8 (1 = duplicate candidate). */
+DSK_API int dsk_band_sums(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint64_t *d_keys, void *stream);
+DSK_API int dsk_bloom_insert(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, uint32_t *d_bits,
+                             uint64_t words_per_table, uint64_t n_bits, int n_hashes, void *stream);
+DSK_API int dsk_bloom_query(const uint32_t *d_sig, int64_t n, int num_perm, int b, int r, const uint32_t *d_bits,
+                            uint64_t words_per_table, uint64_t n_bits, int n_hashes, uint8_t *d_hit, void *stream);
+
 /* ---- Weighted MinHash (Ioffe ICWS) ------------------------------------------------------
  * Handle = device copy of the generator parameters rs, ln_cs, betas, each [sample_size, dim]
  * float32, drawn on the HOST by numpy exactly as WeightedMinHashGenerator.__init__ does

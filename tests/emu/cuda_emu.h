@@ -80,6 +80,7 @@ static inline int atomicCAS(int *p, int cmp, int val) {
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
     return cmp;
 }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
 static inline int atomicExch(int *p, int val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 

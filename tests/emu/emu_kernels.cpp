@@ -16,6 +16,7 @@ thread_local EmuCta *emu_cta = nullptr;
 #include "../../datasketch_b200/csrc/sha1_kernels.cu"
 #include "../../datasketch_b200/csrc/hash_kernels.cu"
 #include "../../datasketch_b200/csrc/wmh_kernels.cu"
+#include "../../datasketch_b200/csrc/bloom_kernels.cu"
 
 #include <vector>
 
