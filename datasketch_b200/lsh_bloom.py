@@ -2,17 +2,19 @@
 
 The reference keeps one Bloom filter per band and keys it with ``x = sum(band hashvalues) % (2**61 - 1)``
 (``BloomTable.insert`` / ``query``, lsh_bloom.py:94-118); it can only answer "is this set a near-duplicate of
-something inserted before?".  Same constructor, validation and ``insert`` / ``query`` behaviour here; the bit
-tables live in HBM (``dsk_bloom_insert`` / ``dsk_bloom_query`` compute the band keys and set / test the probe bits
-in one pass over the signature matrix) and ``insert_batch`` / ``query_batch`` take whole matrices.  The reference
-delegates its bit tables to the optional ``pybloomfilter`` package; these tables are this library's own classic
-k-probe Bloom filters sized by the same ``(n, fp)`` contract -- no false negatives, false-positive rate <= fp at
-n insertions -- not pybloomfilter's mmap file format (``save_dir`` persists them as ``band-tables.npy``).
+something inserted before?".  Same constructor, validation, ``BloomTable`` and ``insert`` / ``query`` / ``sync``
+behaviour here; the bit tables live in HBM (``dsk_bloom_insert`` / ``dsk_bloom_query`` compute the band keys and
+set / test the probe bits in one pass over the signature matrix) and ``insert_batch`` / ``query_batch`` take whole
+matrices.  The reference delegates its bit tables to the optional ``pybloomfilter`` package; these tables are this
+library's own classic k-probe Bloom filters sized by the same ``(item_count, fp)`` contract -- no false negatives,
+false-positive rate <= fp at item_count insertions -- and ``*.bf`` files written by ``sync()`` hold this library's
+format (a 32-byte header + the bit words), not pybloomfilter's mmap layout.
 """
 from __future__ import annotations
 
 import math
 import os
+import struct
 import warnings
 from typing import Optional, Tuple
 
@@ -22,18 +24,89 @@ from . import _native as nv
 from .lsh import _optimal_param, _signature_matrix
 
 _mersenne_prime = np.uint64((1 << 61) - 1)
+_MAGIC = b"DSKBLOOM"
+
+
+def _bloom_size(item_count: int, fp: float) -> Tuple[int, int]:
+    """Classic sizing: m = -n ln fp / (ln 2)^2 bits, k = (m / n) ln 2 probes."""
+    n_bits = max(64, int(math.ceil(-item_count * math.log(fp) / (math.log(2.0) ** 2))))
+    n_hashes = max(1, min(64, int(round(n_bits / item_count * math.log(2.0)))))
+    return n_bits, n_hashes
+
+
+class BloomTable:
+    """One band's Bloom filter (datasketch/lsh_bloom.py:53-118): ``insert(hashvalues)`` / ``query(hashvalues)`` on the
+    r hash values of a band, ``sync()`` to ``fname``.  The bits are a row of a CUDA tensor."""
+
+    def __init__(self, item_count: int, fp: float, band_size: int, fname: Optional[str] = None, device: int = 0,
+                 _bits=None):
+        import torch
+        self.r = band_size
+        self.fname = fname
+        self.device = device
+        self.n_bits, self.n_hashes = _bloom_size(item_count, fp)
+        self.words = (self.n_bits + 31) // 32
+        nv.require_device(device)
+        self.bits = _bits if _bits is not None else torch.zeros((self.words,), dtype=torch.int32,
+                                                                device=torch.device("cuda", device))
+        if fname is not None and os.path.exists(fname):
+            with open(fname, "rb") as f:
+                head = f.read(32)
+                magic, n_bits, n_hashes, words = struct.unpack("<8sQQQ", head)
+                if magic != _MAGIC or (n_bits, n_hashes, words) != (self.n_bits, self.n_hashes, self.words):
+                    raise ValueError("%s does not hold a Bloom table for (item_count=%d, fp=%g)" % (fname, item_count, fp))
+                saved = np.frombuffer(f.read(4 * words), dtype=np.uint32)
+            self.bits.copy_(torch.from_numpy(saved.view(np.int32).copy()))
+
+    def sync(self):
+        if self.fname is None:
+            warnings.warn("Attempting to save in-memory Bloom filter, this is a no-op.", RuntimeWarning, stacklevel=2)
+            return
+        with open(self.fname, "wb") as f:
+            f.write(struct.pack("<8sQQQ", _MAGIC, self.n_bits, self.n_hashes, self.words))
+            f.write(self.bits.cpu().numpy().view(np.uint32).tobytes())
+
+    def assert_size(self, hashvalues):
+        if not len(hashvalues) == self.r:
+            raise RuntimeError(f"Invalid length for indices, {len(hashvalues)}, expected {self.r} hashvalues in band")
+
+    def _row(self, hashvalues):
+        import torch
+        self.assert_size(hashvalues)
+        hv = np.asarray(hashvalues)
+        if hv.size and int(hv.max()) >= (1 << 32):
+            raise ValueError("band hash values must fit 32 bits")
+        return torch.from_numpy(np.ascontiguousarray(hv.astype(np.uint32)).view(np.int32).reshape(1, -1)).cuda(self.device)
+
+    def insert(self, hashvalues) -> None:
+        import torch
+        row = self._row(hashvalues)   # one band of one signature = a [1, r] matrix with b = 1
+        with torch.cuda.device(self.device):
+            nv.check(nv.load().dsk_bloom_insert(row.data_ptr(), 1, self.r, 1, self.r, self.bits.data_ptr(), self.words,
+                                                self.n_bits, self.n_hashes, torch.cuda.current_stream().cuda_stream))
+
+    def query(self, hashvalues) -> bool:
+        import torch
+        row = self._row(hashvalues)
+        hit = torch.zeros((1,), dtype=torch.uint8, device=row.device)
+        with torch.cuda.device(self.device):
+            nv.check(nv.load().dsk_bloom_query(row.data_ptr(), 1, self.r, 1, self.r, self.bits.data_ptr(), self.words,
+                                               self.n_bits, self.n_hashes, hit.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+        return bool(hit.item())
 
 
 def band_keys_host(hashvalues: np.ndarray, b: int, r: int) -> np.ndarray:
-    """The b Bloom keys of ONE signature, on the host, exactly as the reference computes them
+    """The b Bloom keys of ONE signature on the host, exactly as the reference computes them
     (``sum(hashvalues[start:end]) % _mersenne_prime``, lsh_bloom.py:105): API glue for single objects."""
     hv = np.asarray(hashvalues, dtype=np.uint64)
-    return np.array([np.uint64(sum(hv[i * r:(i + 1) * r].tolist()) % int(_mersenne_prime)) for i in range(b)], dtype=np.uint64)
+    return np.array([sum(hv[i * r:(i + 1) * r].tolist()) % int(_mersenne_prime) for i in range(b)], dtype=np.uint64)
 
 
 class MinHashLSHBloom:
     """Drop-in for ``datasketch.MinHashLSHBloom`` (lsh_bloom.py:125): ``insert(minhash)``, ``query(minhash) -> bool``,
-    ``sync()``; plus ``insert_batch(signatures)`` / ``query_batch(signatures) -> bool array`` on [N, K] matrices."""
+    ``sync()``, ``hashtables`` (one ``BloomTable`` per band); plus ``insert_batch(signatures)`` /
+    ``query_batch(signatures) -> bool array`` on [N, K] matrices (one kernel launch each)."""
 
     def __init__(self, threshold: float = 0.9, num_perm: int = 128, n: Optional[int] = None, fp: Optional[float] = None,
                  save_dir: Optional[str] = None, weights: Tuple[float, float] = (0.5, 0.5),
@@ -66,25 +139,22 @@ class MinHashLSHBloom:
             self.b, self.r = _optimal_param(threshold, num_perm, weights[0], weights[1])
         if self.b < 2:
             raise ValueError("The number of bands are too small (b < 2)")
-        self.hashranges = [(i * self.r, (i + 1) * self.r) for i in range(self.b)]
-        # classic Bloom sizing for (n items, false-positive rate fp): m = -n ln fp / (ln 2)^2 bits, k = (m/n) ln 2
-        self.n_bits = max(64, int(math.ceil(-n * math.log(fp) / (math.log(2.0) ** 2))))
-        self.n_hashes = max(1, min(64, int(round(self.n_bits / n * math.log(2.0)))))
-        self.words_per_table = (self.n_bits + 31) // 32
-        self.device = device
-        self.save_dir = save_dir
-        self._bits = None
         import torch
         nv.require_device(device)
+        self.device = device
+        self.save_dir = save_dir
+        self.n_bits, self.n_hashes = _bloom_size(n, fp)
+        self.words_per_table = (self.n_bits + 31) // 32
+        # one [b, words] tensor: the batch kernels address band j's table at row j; each BloomTable is a row view
         self._bits = torch.zeros((self.b, self.words_per_table), dtype=torch.int32, device=torch.device("cuda", device))
         if save_dir is not None:
             os.makedirs(save_dir, exist_ok=True)
-            path = os.path.join(save_dir, "band-tables.npy")
-            if os.path.exists(path):
-                saved = np.load(path)
-                if saved.shape != (self.b, self.words_per_table):
-                    raise ValueError("saved Bloom tables in %s do not match (b, n, fp) of this index" % save_dir)
-                self._bits.copy_(torch.from_numpy(saved.view(np.int32)))
+        self.hashtables = [
+            BloomTable(item_count=n, fp=fp, band_size=self.r,
+                       fname=os.path.join(save_dir, f"band-{i}.bf") if save_dir is not None else None,
+                       device=device, _bits=self._bits[i])
+            for i in range(self.b)]
+        self.hashranges = [(i * self.r, (i + 1) * self.r) for i in range(self.b)]
 
     # ---- whole matrices ---------------------------------------------------------------------------------------
     def _dev_sig(self, sig):
@@ -126,11 +196,12 @@ class MinHashLSHBloom:
     def insert(self, minhash) -> None:
         self.insert_batch(self._row(minhash))
 
+    def _insert(self, minhash) -> None:
+        self.insert(minhash)
+
     def query(self, minhash) -> bool:
         return bool(self.query_batch(self._row(minhash))[0])
 
     def sync(self) -> None:
-        if self.save_dir is None:
-            warnings.warn("Attempting to save in-memory Bloom filter, this is a no-op.", RuntimeWarning, stacklevel=2)
-            return
-        np.save(os.path.join(self.save_dir, "band-tables.npy"), self._bits.cpu().numpy().view(np.uint32))
+        for table in self.hashtables:
+            table.sync()

@@ -15,7 +15,7 @@ band's r hash values as big-endian uint64 bytes (``_H``, lsh.py:537-538), option
 (:540-543).  The band keys of a whole signature matrix come from one ``dsk_band_keys`` launch; everything else is
 dictionary glue on the host.  ``RedisLayout`` holds the three Redis data types as dicts, can replay itself as
 commands into any client with the redis-py pipeline interface, and compares equal to the state the reference itself
-produces on an in-memory stand-in (tests/golden/storage.npz, made by oracle/gen_golden.py).
+produces on an in-memory stand-in (fixture tests/golden/storage.npz).
 """
 from __future__ import annotations
 

@@ -19,6 +19,9 @@ import numpy as np
 
 REF = os.environ.get("DATASKETCH_REF", "/root/reference")
 sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import fake_backends  # noqa: E402  in-memory stand-ins for the optional `redis` / `pybloomfilter` packages
+fake_backends.install()           # must precede the import below: storage.py / lsh_bloom.py probe them at import time
 import datasketch  # noqa: E402  (the reference)
 from datasketch import LeanMinHash, MinHash, MinHashLSH, WeightedMinHashGenerator  # noqa: E402
 
@@ -359,6 +362,57 @@ def gen_forest():
     np.savez_compressed(os.path.join(OUT, "forest.npz"), **d)
 
 
+def gen_bloom():
+    """MinHashLSHBloom (lsh_bloom.py) run on the pybloomfilter stand-in: the values BloomTable.insert hands to the filter
+    ARE the band keys `sum(hashvalues) % _mersenne_prime` (:105); query answers with exact-membership tables."""
+    import warnings
+    from datasketch.lsh_bloom import MinHashLSHBloom
+    sig = np.load(os.path.join(OUT, "lsh.npz"))["sig"]
+    d = {}
+    rows = []
+    for thr, k in [(0.5, 128), (0.8, 128), (0.9, 128), (0.5, 32)]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            l = MinHashLSHBloom(threshold=thr, num_perm=k, n=100, fp=0.01)
+        rows.append([thr, k, l.b, l.r])
+    d["params"] = np.array(rows, dtype=np.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bl = MinHashLSHBloom(threshold=0.8, num_perm=128, n=1000, fp=0.001)
+    d["b_r"] = np.array([bl.b, bl.r], dtype=np.int64)
+    fake_backends.reset()
+    n_ins = 200
+    for row in sig[:n_ins]:
+        bl.insert(LeanMinHash(seed=1, hashvalues=row.astype(np.uint64)))
+    d["keys_inserted"] = np.array([v for _, v in fake_backends.BLOOM_ADDS], dtype=np.uint64).reshape(n_ins, bl.b)
+    d["query_all"] = np.array([bl.query(LeanMinHash(seed=1, hashvalues=row.astype(np.uint64))) for row in sig], dtype=np.bool_)
+    np.savez_compressed(os.path.join(OUT, "bloom.npz"), **d)
+
+
+def gen_storage():
+    """MinHashLSH over the reference's Redis storage (storage.py:819-1049) on the redis stand-in: the database state
+    after the inserts, i.e. the wire layout an existing deployment reads (lsh.py:191-200)."""
+    import pickle
+    sig = np.load(os.path.join(OUT, "lsh.npz"))["sig"]
+    d = {}
+    cases = {"pickled": dict(prepickle=None, keys=[("doc", i) for i in range(120)]),
+             "bytes": dict(prepickle=False, keys=[b"k%04d" % i for i in range(120)])}
+    for name, c in cases.items():
+        fake_backends.reset()
+        lsh = MinHashLSH(threshold=0.8, num_perm=128, prepickle=c["prepickle"],
+                         storage_config={"type": "redis", "basename": b"gpuidx", "redis": {"host": "nowhere", "port": 0}})
+        for key, row in zip(c["keys"], sig):
+            lsh.insert(key, LeanMinHash(seed=1, hashvalues=row.astype(np.uint64)))
+        state = {"hash": {k: dict(v) for k, v in fake_backends.DB["hash"].items()},
+                 "list": {k: list(v) for k, v in fake_backends.DB["list"].items()},
+                 "set": {k: sorted(v) for k, v in fake_backends.DB["set"].items()}}
+        d[name + "_state"] = np.frombuffer(pickle.dumps(state, protocol=4), dtype=np.uint8)
+        d[name + "_b_r"] = np.array([lsh.b, lsh.r], dtype=np.int64)
+        q = sorted(lsh.query(LeanMinHash(seed=1, hashvalues=sig[0].astype(np.uint64))), key=repr)
+        d[name + "_query0"] = np.frombuffer(pickle.dumps(q, protocol=4), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "storage.npz"), **d)
+
+
 if __name__ == "__main__":
     print("reference:", datasketch.__file__)
     gen_minhash()
@@ -370,5 +424,7 @@ if __name__ == "__main__":
     gen_forest()
     gen_ensemble()
     gen_hashes()
+    gen_bloom()
+    gen_storage()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -307,6 +307,36 @@ def lsh_band_keys(hashvalues: np.ndarray, b: int, r: int) -> List[bytes]:
     return [lsh_band_key(hashvalues[s:e]) for s, e in lsh_hashranges(b, r)]
 
 
+def bloom_band_keys(hashvalues: np.ndarray, b: int, r: int) -> np.ndarray:
+    """The b Bloom keys of one signature: ``sum(hashvalues[start:end]) % _mersenne_prime`` per band
+    (datasketch/lsh_bloom.py:105, :116; ``_mersenne_prime`` = 2**61 - 1, :20; hashranges :299)."""
+    hv = np.asarray(hashvalues, dtype=np.uint64)
+    p = (1 << 61) - 1
+    return np.array([sum(int(x) for x in hv[s:e]) % p for s, e in lsh_hashranges(b, r)], dtype=np.uint64)
+
+
+def redis_layout(keys, signatures: np.ndarray, b: int, r: int, basename: bytes, prepickle: bool = True) -> dict:
+    """Database state of the reference's Redis-backed MinHashLSH after ``insert(key_i, signature_i)``:
+    containers ``basename + b"_keys"`` / ``basename + b"_bucket_" + pack(">H", i)`` (datasketch/lsh.py:191-200),
+    ``HSET name key -> name+key`` + ``RPUSH name+key H...`` (storage.py:1002-1004) for the keys container,
+    ``HSET name_i H -> name_i+H`` + ``SADD name_i+H key`` (:1042-1045) per band; keys pickled when prepickle (lsh.py:340-341)."""
+    import pickle
+    import struct
+    state = {"hash": {}, "list": {}, "set": {}}
+    kname = basename + b"_keys"
+    for key, hv in zip(keys, signatures):
+        key = pickle.dumps(key) if prepickle else key
+        hs = lsh_band_keys(np.asarray(hv, dtype=np.uint64), b, r)
+        state["hash"].setdefault(kname, {})[key] = kname + key
+        state["list"].setdefault(kname + key, []).extend(hs)
+        for i, h in enumerate(hs):
+            name = basename + b"_bucket_" + struct.pack(">H", i)
+            state["hash"].setdefault(name, {})[h] = name + h
+            state["set"].setdefault(name + h, set()).add(key)
+    state["set"] = {k: sorted(v) for k, v in state["set"].items()}
+    return state
+
+
 class DictLSH:
     """Dict-storage MinHashLSH insert/query semantics.
 

@@ -201,3 +201,29 @@ def test_token_hashes(golden):
         s32 = int(rs.randint(0, 1 << 32))
         assert hf.murmur3_hash32(d, s32) == o.murmur3_32(d, s32) and hf.xxh32_hash32(d, s32) == o.xxh32(d, s32)
     assert hf.sha1_hash32(b"Hello") == o.sha1_hash32(b"Hello")
+
+
+def test_bloom_band_keys_and_redis_layout(golden):
+    """The oracle's LSHBloom keys and Redis layout against what the reference's own code wrote when it ran on the
+    in-memory stand-ins for pybloomfilter / redis (oracle/gen_golden.py: gen_bloom, gen_storage)."""
+    import pickle
+    sig = golden("lsh")["sig"]
+    g = golden("bloom")
+    b, r = (int(x) for x in g["b_r"])
+    keys = g["keys_inserted"]
+    for i in range(len(keys)):
+        assert np.array_equal(o.bloom_band_keys(sig[i].astype(np.uint64), b, r), keys[i])
+    for thr, k, bb, rr in g["params"]:
+        assert o.lsh_optimal_param(float(thr), int(k)) == (int(bb), int(rr))
+    # exact-membership tables: a row is a duplicate iff one of its band keys was inserted for that band
+    seen = [set(keys[:, j].tolist()) for j in range(b)]
+    want = [any(int(x) in seen[j] for j, x in enumerate(o.bloom_band_keys(row.astype(np.uint64), b, r))) for row in sig]
+    assert want == g["query_all"].tolist() and all(want[:len(keys)]) and not all(want)
+    s = golden("storage")
+    for name, mk in (("pickled", lambda i: ("doc", i)), ("bytes", lambda i: b"k%04d" % i)):
+        state = pickle.loads(s[name + "_state"].tobytes())
+        bb, rr = (int(x) for x in s[name + "_b_r"])
+        got = o.redis_layout([mk(i) for i in range(120)], sig[:120].astype(np.uint64), bb, rr, b"gpuidx",
+                             prepickle=(name == "pickled"))
+        assert got == state
+        assert set(state["hash"]) == {b"gpuidx_keys"} | {b"gpuidx_bucket_" + bytes([0, i]) for i in range(bb)}
