@@ -38,10 +38,14 @@ SIGNATURES = {
     "dsk_perm_analyze": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "dsk_minhash_bulk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),
+    "dsk_minhash_bulk_workspace_size": (ctypes.c_size_t, [c_int64, c_int64]),
+    "dsk_minhash_bulk_ws": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
+                                    c_void_p, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
     "dsk_minhash_bulk_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int,
                                         c_int64, c_int, c_int, c_void_p]),
     "dsk_minhash_bulk_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_void_p, c_int, c_int]),
+    "dsk_release_host_pipeline": (c_int, [c_int]),
     "dsk_sig_merge_min": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dsk_wmh_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "dsk_wmh_destroy": (None, [c_void_p]),

@@ -106,13 +106,38 @@ struct dsk_perm {
     int n_unsafe = 0;
     uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi | b_lo + 7, each kpad entries
     unsigned *d_counters = nullptr;  // kCounterSets x kCounterStride work counters (one set per in-flight launch)
-    mutable std::atomic<unsigned> next_set{0};
+    // A launch leases one counter set; the event recorded behind the launch makes the NEXT user of that set wait
+    // (stream-ordered, on the device) until the kernel that still reads it has finished -- 64+ launches of one handle
+    // outstanding on different streams would otherwise share counters and skip documents.
+    mutable std::mutex mu;
+    mutable unsigned next_set = 0;
+    mutable cudaEvent_t ev[64] = {};
+    mutable bool ev_live[64] = {};
     std::vector<uint64_t> a, b;
 };
 static constexpr int kCounterSets = 64, kCounterStride = 64;
-static unsigned *perm_counters(const dsk_perm *p) {
-    return p->d_counters + (size_t)(p->next_set.fetch_add(1) % kCounterSets) * kCounterStride;
-}
+
+// lease a counter set for one launch on stream s: holds the handle's mutex from acquire to release so that the
+// wait -> launch -> record sequence of concurrent host threads cannot interleave
+struct CounterLease {
+    const dsk_perm *p;
+    int set;
+    cudaStream_t s;
+    unsigned *ptr;
+    CounterLease(const dsk_perm *perm, cudaStream_t stream) : p(perm), s(stream) {
+        p->mu.lock();
+        set = (int)(p->next_set++ % kCounterSets);
+        if (p->ev_live[set]) cudaStreamWaitEvent(s, p->ev[set], 0);
+        ptr = p->d_counters + (size_t)set * kCounterStride;
+    }
+    ~CounterLease() {
+        if (!p->ev[set]) {
+            if (cudaEventCreateWithFlags(&p->ev[set], cudaEventDisableTiming) != cudaSuccess) p->ev[set] = nullptr;
+        }
+        p->ev_live[set] = p->ev[set] && cudaEventRecord(p->ev[set], s) == cudaSuccess;
+        p->mu.unlock();
+    }
+};
 
 struct dsk_wmh {
     int device = 0, ss = 0, ss_pad = 0, dim = 0;
@@ -232,6 +257,8 @@ void dsk_perm_destroy(dsk_perm *p) {
         cudaSetDevice(p->device);
         cudaFree(p->d_tab);
         if (p->d_counters) cudaFree(p->d_counters);
+        for (int i = 0; i < kCounterSets; ++i)
+            if (p->ev[i]) cudaEventDestroy(p->ev[i]);
         cudaSetDevice(prev);
     }
     delete p;
@@ -255,11 +282,28 @@ static int pick_mode(const dsk_perm *perm, int token_is_u64, int flags, int *mod
     }
 }
 
+size_t dsk_minhash_bulk_workspace_size(int64_t n_docs, int64_t n_tokens) {
+    (void)n_docs;
+    return n_tokens < 0 ? 0 : minhash_sig_workspace_bytes(n_tokens);
+}
+
 int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u64, const int64_t *d_offsets,
                      int64_t n_docs, int64_t n_tokens, const void *d_init, int64_t init_stride, int init_is_u64,
                      void *d_out, int out_is_u64, int flags, void *stream) {
+    return dsk_minhash_bulk_ws(perm, d_tokens, token_is_u64, d_offsets, n_docs, n_tokens, d_init, init_stride, init_is_u64,
+                               d_out, out_is_u64, flags, nullptr, 0, stream);
+}
+
+int dsk_minhash_bulk_ws(const dsk_perm *perm, const void *d_tokens, int token_is_u64, const int64_t *d_offsets,
+                        int64_t n_docs, int64_t n_tokens, const void *d_init, int64_t init_stride, int init_is_u64,
+                        void *d_out, int out_is_u64, int flags, void *d_workspace, size_t workspace_bytes, void *stream) {
     if (!perm || !d_offsets || !d_out || n_docs < 0 || n_tokens < 0 || (n_tokens > 0 && !d_tokens)) {
         set_error("dsk_minhash_bulk: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (d_workspace && (((uintptr_t)d_workspace & 15) != 0 || workspace_bytes < minhash_sig_workspace_bytes(n_tokens))) {
+        set_error("dsk_minhash_bulk_ws: workspace must be 16-byte aligned and hold dsk_minhash_bulk_workspace_size() = %zu bytes",
+                  minhash_sig_workspace_bytes(n_tokens));
         return DSK_ERR_INVALID;
     }
     if (n_docs == 0) return DSK_OK;
@@ -277,7 +321,7 @@ int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u6
     DevInfo *dev;
     rc = get_dev(perm->device, &dev);
     if (rc) return rc;
-    BulkParams prm;
+    BulkParams prm{};
     prm.tokens = d_tokens;
     prm.offsets = d_offsets;
     prm.n_docs = n_docs;
@@ -293,10 +337,17 @@ int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int token_is_u6
     prm.init_is_u64 = init_is_u64;
     prm.out = d_out;
     prm.out_is_u64 = out_is_u64;
-    prm.work_counter = perm_counters(perm);
     prm.docs_per_unit = 0;
     prm.n_peers = 0;
     prm.peer_row_offset = 0;
+    if (d_workspace && minhash_sig_workspace_bytes(n_tokens) > 0) {   // long documents are cut into pieces on the device
+        prm.long_doc_tokens = kLongDocTokensApi;
+        prm.piece_tokens = kPieceTokensApi;
+        prm.piece_hdr = static_cast<unsigned *>(d_workspace);
+        prm.pieces = reinterpret_cast<PieceDesc *>(static_cast<char *>(d_workspace) + kPieceHdrBytes);
+    }
+    CounterLease lease(perm, (cudaStream_t)stream);
+    prm.work_counter = lease.ptr;
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
     return DSK_OK;
 }
@@ -320,7 +371,7 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
     DevInfo *dev;
     rc = get_dev(perm->device, &dev);
     if (rc) return rc;
-    BulkParams prm;
+    BulkParams prm{};
     prm.tokens = d_tokens;
     prm.offsets = d_offsets;
     prm.n_docs = n_docs;
@@ -336,7 +387,6 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
     prm.init_is_u64 = 0;
     prm.out = nullptr;
     prm.out_is_u64 = out_is_u64;
-    prm.work_counter = perm_counters(perm);
     prm.docs_per_unit = 0;
     prm.n_peers = n_peers;
     prm.peer_row_offset = row_offset;
@@ -346,6 +396,8 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
             set_error("dsk_minhash_bulk_gather: peer pointer %d is null or not 16-byte aligned", i);
             return DSK_ERR_ALIGN;
         }
+    CounterLease lease(perm, (cudaStream_t)stream);
+    prm.work_counter = lease.ptr;
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
     return DSK_OK;
 }
@@ -555,7 +607,7 @@ void dsk_wmh_destroy(dsk_wmh *g) {
 
 int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_out, int32_t *d_status, int flags,
                     void *stream) {
-    if (!g || n < 0 || (flags != DSK_WMH_MINHASH && flags != DSK_WMH_MINHASH_MANY) || (n > 0 && (!d_v || !d_out || !d_status))) {
+    if (!g || n < 0 || (flags & ~(DSK_WMH_MINHASH_MANY | DSK_WMH_INPUT_LOG)) != 0 || (n > 0 && (!d_v || !d_out || !d_status))) {
         set_error("dsk_wmh_minhash: bad arguments");
         return DSK_ERR_INVALID;
     }
@@ -564,7 +616,8 @@ int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_ou
     if (rc) return rc;
     const size_t plane = (size_t)g->dim * g->ss_pad;
     DSK_CUDA(launch_wmh(g->d_par, g->d_par + plane, g->d_par + 2 * plane, g->ss, g->ss_pad, g->dim, d_v, n, d_out,
-                        d_status, flags == DSK_WMH_MINHASH_MANY, dev->sm_count, (cudaStream_t)stream));
+                        d_status, (flags & DSK_WMH_MINHASH_MANY) != 0, (flags & DSK_WMH_INPUT_LOG) != 0, dev->sm_count,
+                        (cudaStream_t)stream));
     return DSK_OK;
 }
 
@@ -798,6 +851,7 @@ int dsk_forest_query(const uint32_t *d_sig, const int32_t *d_order, int64_t n, i
 }
 
 // ---- host-buffer pipeline --------------------------------------------------------------------
+extern "C++" {
 namespace {
 constexpr int kSlots = 3;
 struct HostPipe {
@@ -812,10 +866,41 @@ struct HostPipe {
     uint32_t *d_part[kSlots] = {};
     int64_t *d_seg[kSlots] = {};
     int64_t *h_seg[kSlots] = {};
-    size_t cap_tok = 0, cap_docs = 0, cap_out = 0, cap_init = 0, cap_part = 0, cap_seg = 0;
+    size_t cap_tok = 0, cap_off_dev = 0, cap_off_host = 0, cap_out = 0, cap_init = 0, cap_part = 0, cap_seg_dev = 0,
+           cap_seg_host = 0;   // bytes per slot of each buffer class
 };
 HostPipe g_pipe[64];
 std::mutex g_pipe_mu;
+
+// one buffer class of the pipeline (kSlots buffers of equal capacity); a failed (re)allocation leaves it EMPTY
+// (all slots null, capacity 0), so the next call allocates again instead of copying to a null pointer
+template <typename T>
+int pipe_grow(T *(&slot)[kSlots], size_t &cap, size_t want_bytes, bool pinned) {
+    if (want_bytes <= cap) return DSK_OK;
+    for (int i = 0; i < kSlots; ++i) {
+        if (slot[i]) {
+            if (pinned) cudaFreeHost(slot[i]);
+            else cudaFree(slot[i]);
+        }
+        slot[i] = nullptr;
+    }
+    cap = 0;
+    for (int i = 0; i < kSlots; ++i) {
+        void *ptr = nullptr;
+        const cudaError_t e = pinned ? cudaMallocHost(&ptr, want_bytes + 64) : cudaMalloc(&ptr, want_bytes + 64);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < i; ++q) {
+                if (pinned) cudaFreeHost(slot[q]);
+                else cudaFree(slot[q]);
+                slot[q] = nullptr;
+            }
+            return cuda_fail(e, "host pipeline buffer allocation");
+        }
+        slot[i] = static_cast<T *>(ptr);
+    }
+    cap = want_bytes;
+    return DSK_OK;
+}
 
 int pipe_reserve(HostPipe &hp, int device, size_t tok_bytes, size_t docs, size_t out_bytes, size_t init_bytes,
                  size_t part_bytes, size_t seg_docs) {
@@ -823,63 +908,54 @@ int pipe_reserve(HostPipe &hp, int device, size_t tok_bytes, size_t docs, size_t
         for (int i = 0; i < kSlots; ++i) DSK_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
         hp.device = device;
     }
-    if (tok_bytes > hp.cap_tok) {
-        for (int i = 0; i < kSlots; ++i) {
-            if (hp.d_tok[i]) cudaFree(hp.d_tok[i]);
-            hp.d_tok[i] = nullptr;
-            DSK_CUDA(cudaMalloc(&hp.d_tok[i], tok_bytes + 64));
-        }
-        hp.cap_tok = tok_bytes;
+    int rc;
+    if ((rc = pipe_grow(hp.d_tok, hp.cap_tok, tok_bytes, false))) return rc;
+    const size_t off_bytes = (docs + 1) * sizeof(int64_t);
+    if (off_bytes > hp.cap_off_dev && (rc = pipe_grow(hp.d_off, hp.cap_off_dev, off_bytes, false))) return rc;
+    if (off_bytes > hp.cap_off_host && (rc = pipe_grow(hp.h_off, hp.cap_off_host, off_bytes, true))) return rc;
+    if ((rc = pipe_grow(hp.d_out, hp.cap_out, out_bytes, false))) return rc;
+    if (part_bytes && (rc = pipe_grow(hp.d_part, hp.cap_part, part_bytes, false))) return rc;
+    if (seg_docs) {
+        const size_t seg_bytes = (seg_docs + 1) * sizeof(int64_t);
+        if ((rc = pipe_grow(hp.d_seg, hp.cap_seg_dev, seg_bytes, false))) return rc;
+        if ((rc = pipe_grow(hp.h_seg, hp.cap_seg_host, seg_bytes, true))) return rc;
     }
-    if (docs > hp.cap_docs) {
-        for (int i = 0; i < kSlots; ++i) {
-            if (hp.d_off[i]) cudaFree(hp.d_off[i]);
-            if (hp.h_off[i]) cudaFreeHost(hp.h_off[i]);
-            hp.d_off[i] = nullptr;
-            hp.h_off[i] = nullptr;
-            DSK_CUDA(cudaMalloc(&hp.d_off[i], (docs + 1) * sizeof(int64_t)));
-            DSK_CUDA(cudaMallocHost(&hp.h_off[i], (docs + 1) * sizeof(int64_t)));
-        }
-        hp.cap_docs = docs;
-    }
-    if (out_bytes > hp.cap_out) {
-        for (int i = 0; i < kSlots; ++i) {
-            if (hp.d_out[i]) cudaFree(hp.d_out[i]);
-            hp.d_out[i] = nullptr;
-            DSK_CUDA(cudaMalloc(&hp.d_out[i], out_bytes + 64));
-        }
-        hp.cap_out = out_bytes;
-    }
-    if (part_bytes > hp.cap_part) {
-        for (int i = 0; i < kSlots; ++i) {
-            if (hp.d_part[i]) cudaFree(hp.d_part[i]);
-            hp.d_part[i] = nullptr;
-            DSK_CUDA(cudaMalloc(&hp.d_part[i], part_bytes + 64));
-        }
-        hp.cap_part = part_bytes;
-    }
-    if (seg_docs > hp.cap_seg) {
-        for (int i = 0; i < kSlots; ++i) {
-            if (hp.d_seg[i]) cudaFree(hp.d_seg[i]);
-            if (hp.h_seg[i]) cudaFreeHost(hp.h_seg[i]);
-            hp.d_seg[i] = nullptr;
-            hp.h_seg[i] = nullptr;
-            DSK_CUDA(cudaMalloc(&hp.d_seg[i], (seg_docs + 1) * sizeof(int64_t)));
-            DSK_CUDA(cudaMallocHost(&hp.h_seg[i], (seg_docs + 1) * sizeof(int64_t)));
-        }
-        hp.cap_seg = seg_docs;
-    }
-    if (init_bytes > hp.cap_init) {
-        for (int i = 0; i < kSlots; ++i) {
-            if (hp.d_init[i]) cudaFree(hp.d_init[i]);
-            hp.d_init[i] = nullptr;
-            DSK_CUDA(cudaMalloc(&hp.d_init[i], init_bytes + 64));
-        }
-        hp.cap_init = init_bytes;
-    }
+    if (init_bytes && (rc = pipe_grow(hp.d_init, hp.cap_init, init_bytes, false))) return rc;
     return DSK_OK;
 }
+
+void pipe_release(HostPipe &hp) {
+    if (hp.device < 0) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(hp.device);
+    for (int i = 0; i < kSlots; ++i) {
+        if (hp.stream[i]) { cudaStreamSynchronize(hp.stream[i]); cudaStreamDestroy(hp.stream[i]); }
+        if (hp.d_tok[i]) cudaFree(hp.d_tok[i]);
+        if (hp.d_off[i]) cudaFree(hp.d_off[i]);
+        if (hp.d_out[i]) cudaFree(hp.d_out[i]);
+        if (hp.d_init[i]) cudaFree(hp.d_init[i]);
+        if (hp.d_part[i]) cudaFree(hp.d_part[i]);
+        if (hp.d_seg[i]) cudaFree(hp.d_seg[i]);
+        if (hp.h_off[i]) cudaFreeHost(hp.h_off[i]);
+        if (hp.h_seg[i]) cudaFreeHost(hp.h_seg[i]);
+    }
+    hp = HostPipe();
+    cudaSetDevice(prev);
+}
 }  // namespace
+}  // extern "C++"
+
+int dsk_release_host_pipeline(int device) {
+    if (device < -1 || device >= 64) {
+        set_error("dsk_release_host_pipeline: device must be -1 (all) or a device index");
+        return DSK_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    for (int d = 0; d < 64; ++d)
+        if (device < 0 || d == device) pipe_release(g_pipe[d]);
+    return DSK_OK;
+}
 
 int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_is_u64, const int64_t *h_offsets,
                           int64_t n_docs, const void *h_init, int64_t init_stride, int init_is_u64, void *h_out,
@@ -969,7 +1045,7 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         return rc;
     }
 
-    BulkParams prm;
+    BulkParams prm{};
     prm.a_lo = perm->d_tab;
     prm.a_hi = perm->d_tab + perm->kpad;
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
@@ -1030,10 +1106,11 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
         prm.offsets = hp.d_off[slot];
         prm.n_docs = n_ext;
         prm.n_tokens = nt;
-        prm.work_counter = perm_counters(perm);
         prm.docs_per_unit = 0;
         prm.n_peers = 0;
         prm.peer_row_offset = 0;
+        CounterLease lease(perm, st);
+        prm.work_counter = lease.ptr;
         if (!split) {
             prm.init = slice_init;
             prm.out = hp.d_out[slot];

@@ -56,10 +56,22 @@ struct BulkParams {
     int n_peers;
     int64_t peer_row_offset;
     void *peer_out[8];
+    // long documents (signature_kernel.cu): a document longer than long_doc_tokens is not processed by the warp that
+    // meets it; the warp stores the row's initial value and appends ceil(len / piece_tokens) PieceDesc entries, which a
+    // second launch of the kernel in piece mode spreads over all warps and min-merges into the row with atomicMin.
+    int64_t long_doc_tokens;    // 0 = never defer
+    int piece_tokens;
+    unsigned *piece_hdr;        // [0] = pieces appended so far; [64 + K-slice] = work counters of the piece-mode launch
+    struct PieceDesc *pieces;   // capacity guaranteed by the launcher: n_tokens / piece_tokens + n_tokens / long_doc_tokens + 1
 };
+struct PieceDesc { int64_t row, start, end, reserved; };
+constexpr int kPieceHdrBytes = 512;
+constexpr int64_t kLongDocTokensApi = 16384;   // documents longer than this are cut into pieces of kPieceTokensApi tokens
+constexpr int kPieceTokensApi = 4096;
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
 cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s);   // signature_kernel.cu (two-phase)
+size_t minhash_sig_workspace_bytes(int64_t n_tokens);   // piece table for long documents (0 if none can occur)
 cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
                            int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,
                            cudaStream_t s);
@@ -84,7 +96,7 @@ cudaError_t launch_bloom_query(const uint32_t *sig, int64_t n, int k, int b, int
 
 cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, float *dst, cudaStream_t s);
 cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *betas_t, int ss, int ss_pad, int dim,
-                       const float *v, int64_t n, int64_t *out, int32_t *status, int many, int sm_count,
+                       const float *v, int64_t n, int64_t *out, int32_t *status, int many, int input_log, int sm_count,
                        cudaStream_t s);
 
 // ---- device-resident LSH index (lsh_kernels.cu) -------------------------------------------------

@@ -14,7 +14,8 @@
 //            multiple of 16 tokens long and does not wrap the ring is used in place; any other one is copied
 //            (and re-aligned, padded to a multiple of 16 with a duplicate of its last token -- min is idempotent)
 //            into a per-warp line buffer by the lanes.  When the warp has seen repeated tokens it also DEDUPLICATES
-//            during that copy (a 1024-slot shared-memory hash set, atomicCAS): the signature of a multiset is the
+//            during that copy (a 1024-slot shared-memory table, one atomicExch per token, no probing: the first
+//            copy of a token always survives, most later copies are dropped): the signature of a multiset is the
 //            signature of its support, and distinct tokens cannot tie.
 //   phase 1  per 16-token block: 16 IMAD (L') + 8 VIMNMX3 per permutation, then four tracking ops on
 //            key = (block min & ~31) | block index:  m = smallest key, m2 = second smallest.
@@ -24,7 +25,7 @@
 //            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp, two permutations
 //            at a time: every lane filters 1/32 of the sub-piece's tokens with L' and evaluates r exactly for the
 //            ones inside the window, then one redux.sync.min.  Exact for any input; ~40 issue slots per flagged
-//            (document, permutation).  A sub-piece with >= 24 flagged permutations (heavy repetition) switches the
+//            (document, permutation).  A sub-piece with >= 8 flagged permutations (repeated tokens) switches the
 //            warp to de-duplicating staging, which removes the ties at their source.
 #include "dsk_common.cuh"
 
@@ -40,7 +41,7 @@ constexpr int kTabSlots = 1024;     // dedupe hash set (load factor <= 0.5)
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kKeyMask = 31u;  // low bits of a tracking key hold the block index (32 blocks of 16 tokens)
 constexpr uint32_t kNearWindow = 7u + 2u * kKeyMask;  // m2 - m <= this: another block may be inside the +7 window
-constexpr int kDedupeOnFlags = 24;  // flagged permutations in one sub-piece (of 32*P) that switch de-duplication on
+constexpr int kDedupeOnFlags = 8;   // flagged permutations in one sub-piece (of 32*P) that switch de-duplication on
 
 // Path counters for the CPU emulation tests (tests/emu): which staging path / how many flagged permutations.
 // The product build compiles them away.
@@ -71,7 +72,7 @@ __device__ __forceinline__ void load_block16(const uint32_t *src, uint32_t (&t)[
     }
 }
 
-template <int P, int OCC>
+template <int P, int OCC, bool PIECES>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
     __shared__ __align__(128) uint32_t s_ring[kSigWarps][kRingTok];
     __shared__ __align__(128) uint32_t s_buf[kSigWarps][kSubTok];
@@ -83,7 +84,11 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
     const int64_t *__restrict__ offsets = prm.offsets;
     const int K = prm.k;
     const int kl = blockIdx.y * (32 * P) + lane * P;  // first permutation owned by this lane
-    const int64_t n_docs = prm.n_docs, n_tokens = prm.n_tokens;
+    // piece mode (second launch, long documents): the work items are the PieceDesc entries the first launch appended
+    const int64_t n_docs = PIECES ? (int64_t)*reinterpret_cast<const volatile unsigned *>(prm.piece_hdr) : prm.n_docs;
+    const int64_t n_tokens = prm.n_tokens;
+    unsigned *const work_counter = PIECES ? prm.piece_hdr + 64 : prm.work_counter;
+    const int docs_per_unit = PIECES ? 1 : prm.docs_per_unit;
 
     // c7 = b_lo + 7 is what the hot loop adds; b_lo = c7 - 7 is rebuilt where the exact evaluation needs it
     uint32_t alo[P], ahi[P], c7[P], bhi[P];
@@ -115,12 +120,18 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
 
     while (true) {
         int64_t unit = 0;
-        if (lane == 0) unit = (int64_t)atomicAdd(prm.work_counter + blockIdx.y, 1u);
+        if (lane == 0) unit = (int64_t)atomicAdd(work_counter + blockIdx.y, 1u);
         unit = __shfl_sync(0xFFFFFFFFu, unit, 0);
-        const int64_t dlo = unit * prm.docs_per_unit;
+        const int64_t dlo = unit * docs_per_unit;
         if (dlo >= n_docs) break;
-        const int64_t dhi = min(dlo + (int64_t)prm.docs_per_unit, n_docs);
-        const int64_t tok_lo = __ldg(offsets + dlo), tok_hi = __ldg(offsets + dhi);
+        const int64_t dhi = min(dlo + (int64_t)docs_per_unit, n_docs);
+        int64_t tok_lo, tok_hi, piece_row = 0;
+        if constexpr (PIECES) {
+            const PieceDesc pd = prm.pieces[dlo];
+            tok_lo = pd.start; tok_hi = pd.end; piece_row = pd.row;
+        } else {
+            tok_lo = __ldg(offsets + dlo); tok_hi = __ldg(offsets + dhi);
+        }
         int64_t c_next = tok_lo >> kChunkShift;                 // next chunk to issue
         int64_t c_wait = c_next;                                // next chunk to wait for
         const int64_t c_last = (tok_hi - 1) >> kChunkShift;     // last chunk this unit touches (if it has tokens)
@@ -129,6 +140,16 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
         // earlier sub-piece is finished), so up to three chunks beyond it can be in flight.
         auto ensure = [&](int64_t s, int64_t e) {
             const int64_t cf = s >> kChunkShift, cl = (e - 1) >> kChunkShift;
+            if (c_wait < cf) {   // tokens were skipped (a deferred long document): drain what is in flight, jump ahead
+                while (c_wait < cf && c_wait < c_next) {
+                    const int slot = (int)(c_wait & (kRingSlots - 1));
+                    mbar_wait(&bar[slot], (par_mask >> slot) & 1u);
+                    par_mask ^= 1u << slot;
+                    ++c_wait;
+                }
+                c_wait = cf;
+                if (c_next < cf) c_next = cf;
+            }
             const int64_t lim = min(cf + (kRingSlots - 1), c_last);
             if (c_next <= lim) {
                 __syncwarp();   // every lane is done reading the chunks these copies overwrite (in-place sub-pieces)
@@ -163,16 +184,34 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
         };
 
         int64_t start = tok_lo;
-        int64_t end_pref = __ldg(offsets + dlo + 1);  // offsets are read one document ahead
+        int64_t end_pref = PIECES ? tok_hi : __ldg(offsets + dlo + 1);  // offsets are read one document ahead
         for (int64_t d = dlo; d < dhi; ++d) {
             const int64_t end = end_pref;
-            if (d + 1 < dhi) end_pref = __ldg(offsets + d + 2);
+            if (!PIECES && d + 1 < dhi) end_pref = __ldg(offsets + d + 2);
 
             uint32_t acc[P];
 #pragma unroll
             for (int j = 0; j < P; ++j) acc[j] = 0xFFFFFFFFu;
 
-            for (int64_t s = start; s < end; s += kSubTok) {
+            // a long document is cut into pieces for the second launch; here only its initial row gets stored below
+            bool defer = false;
+            if constexpr (!PIECES) {
+                defer = prm.long_doc_tokens > 0 && end - start > prm.long_doc_tokens;
+                if (defer && blockIdx.y == 0) {
+                    const int64_t np = (end - start + prm.piece_tokens - 1) / prm.piece_tokens;
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(prm.piece_hdr, (unsigned)np);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    for (int64_t q = lane; q < np; q += 32) {
+                        PieceDesc pd;
+                        pd.row = d; pd.start = start + q * prm.piece_tokens;
+                        pd.end = min(end, pd.start + (int64_t)prm.piece_tokens); pd.reserved = 0;
+                        prm.pieces[base + q] = pd;
+                    }
+                }
+            }
+
+            for (int64_t s = start; s < (defer ? start : end); s += kSubTok) {
                 const int len = (int)min((int64_t)kSubTok, end - s);
                 ensure(s, s + len);
                 const uint32_t rpos = (uint32_t)s & (kRingTok - 1);
@@ -195,23 +234,17 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         for (int q = 0; q < kTabSlots / 128; ++q)
                             t4[q * 32 + lane] = make_uint4(kEmptySlot, kEmptySlot, kEmptySlot, kEmptySlot);
                         __syncwarp();
+                        // One atomicExch per token, no probing: a token is dropped iff the exchange returns the token
+                        // itself, i.e. an earlier copy of it already went through this slot -- so the first copy always
+                        // survives (exact), while a copy whose slot was meanwhile taken by another token survives too
+                        // (a missed repeat only costs a flagged permutation later).  The marker value itself is kept.
                         int base = 0;
                         for (int i0 = 0; i0 < len; i0 += 32) {
                             const int i = i0 + lane;
                             bool keep = i < len;
-                            uint32_t t = 0;
-                            if (keep) {
-                                t = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
-                                if (t != kEmptySlot) {   // (a token equal to the empty marker is simply kept)
-                                    uint32_t slot = (t * 0x9E3779B1u) >> 22;
-                                    while (true) {
-                                        const uint32_t old = atomicCAS(&tab[slot], kEmptySlot, t);
-                                        if (old == kEmptySlot) break;               // first occurrence
-                                        if (old == t) { keep = false; break; }      // seen before
-                                        slot = (slot + 1) & (kTabSlots - 1);
-                                    }
-                                }
-                            }
+                            uint32_t t = kEmptySlot;
+                            if (keep) t = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
+                            if (t != kEmptySlot) keep = atomicExch(&tab[(t * 0x9E3779B1u) >> 22], t) != t;
                             const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
                             if (keep) buf[base + __popc(bal & ((1u << lane) - 1u))] = t;
                             base += __popc(bal);
@@ -375,7 +408,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
             }
 
             // ---- merge with the running state (minhash.py:297) and store ---------------------------
-            if (prm.init != nullptr) {
+            if (!PIECES && prm.init != nullptr) {
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
                     if (kl + j < K) {
@@ -388,6 +421,21 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         }
                     }
                 }
+            }
+            if constexpr (PIECES) {   // min-merge this piece into the row the first launch initialised
+                if (prm.out_is_u64) {
+                    unsigned long long *row = static_cast<unsigned long long *>(prm.out) + piece_row * (int64_t)K + kl;
+#pragma unroll
+                    for (int j = 0; j < P; ++j)
+                        if (kl + j < K) atomicMin(row + j, (unsigned long long)acc[j]);
+                } else {
+                    uint32_t *row = static_cast<uint32_t *>(prm.out) + piece_row * (int64_t)K + kl;
+#pragma unroll
+                    for (int j = 0; j < P; ++j)
+                        if (kl + j < K) atomicMin(row + j, acc[j]);
+                }
+                start = end;
+                continue;
             }
             // One store per destination: the caller's matrix, or -- fused all-gather -- the same row of the full
             // [N_total, K] matrix on EVERY rank (peer pointers mapped over NVLink; plain st.global to a peer address).
@@ -421,6 +469,16 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
     }  // units
 }
 
+constexpr int64_t kLongDocTokens = kLongDocTokensApi;
+constexpr int kPieceTokens = kPieceTokensApi;
+
+// bytes of the piece table a launch over n_tokens tokens can need (0: no document can be long enough)
+size_t minhash_sig_workspace_bytes(int64_t n_tokens) {
+    if (n_tokens <= kLongDocTokens) return 0;
+    const int64_t cap = n_tokens / kPieceTokens + n_tokens / kLongDocTokens + 2;
+    return (size_t)kPieceHdrBytes + (size_t)cap * sizeof(PieceDesc);
+}
+
 template <int P, int OCC>
 static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
     BulkParams prm = prm_in;
@@ -435,10 +493,22 @@ static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream
         int64_t dpu = prm.n_docs / (gx * kSigWarps * 8);
         prm.docs_per_unit = (int)(dpu < 1 ? 1 : (dpu > 32 ? 32 : dpu));
     }
+    // long documents: only with a caller-provided piece table, plain (non-gather) output
+    const bool split = prm.piece_hdr != nullptr && prm.n_peers == 0 && prm.n_tokens > prm.long_doc_tokens && prm.long_doc_tokens > 0;
+    if (!split) prm.long_doc_tokens = 0;
     cudaError_t e = cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned) * (size_t)slices, s);
     if (e != cudaSuccess) return e;
+    if (split) {
+        e = cudaMemsetAsync(prm.piece_hdr, 0, kPieceHdrBytes, s);
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid((unsigned)gx, (unsigned)slices);
-    DSK_LAUNCH((minhash_sig_kernel<P, OCC>), grid, kSigWarps * 32, 0, s, prm);
+    DSK_LAUNCH((minhash_sig_kernel<P, OCC, false>), grid, kSigWarps * 32, 0, s, prm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !split) return e;
+    // second launch: the pieces (their number is only known on the device; an empty table costs one idle launch)
+    dim3 pgrid((unsigned)gmax, (unsigned)slices);
+    DSK_LAUNCH((minhash_sig_kernel<P, OCC, true>), pgrid, kSigWarps * 32, 0, s, prm);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ struct WmhParams {
     int64_t n;
     int64_t *out;                          // [n][ss][2]
     int32_t *status;                       // [n]: 1 = all-zero input (weighted_minhash.py:149-150)
+    int input_log;                         // v already holds ln(weight) as float32 (NaN where the weight is zero)
 };
 
 // ln_a for one (sample, dim): each float32 operation rounded separately, in the reference's order
@@ -71,7 +72,10 @@ __global__ void __launch_bounds__(kWmhThreads) wmh_kernel(const WmhParams p) {
                 float lg = __int_as_float(0x7fc00000);  // NaN: padding and zero weights are skipped
                 if (dd < nd && u0 + u < p.n) {
                     const float x = __ldg(p.v + (u0 + u) * (int64_t)p.dim + d0 + dd);
-                    if (x != 0.f) lg = (float)log((double)x);
+                    // host-computed logarithms (numpy's own float32 log: bit-identical to the reference by
+                    // construction) or, opt-in, the device's correctly rounded one (<= 1 ulp from numpy's)
+                    if (p.input_log) lg = x;
+                    else if (x != 0.f) lg = (float)log((double)x);
                 }
                 s_vlog[dd][u] = lg;
             }
@@ -154,10 +158,11 @@ cudaError_t launch_wmh_transpose(const float *src, int ss, int dim, int ss_pad, 
 }
 
 cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *betas_t, int ss, int ss_pad, int dim,
-                       const float *v, int64_t n, int64_t *out, int32_t *status, int many, int sm_count,
+                       const float *v, int64_t n, int64_t *out, int32_t *status, int many, int input_log, int sm_count,
                        cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     WmhParams p;
+    p.input_log = input_log;
     p.rs_t = rs_t; p.lncs_t = lncs_t; p.betas_t = betas_t;
     p.ss = ss; p.ss_pad = ss_pad; p.dim = dim; p.v = v; p.n = n; p.out = out; p.status = status;
     const int64_t groups = (n + kVec - 1) / kVec;

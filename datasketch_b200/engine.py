@@ -59,14 +59,15 @@ def bulk_signatures(tokens, offsets, permutations: np.ndarray, init: Optional[np
     H2D -> kernel -> D2H on internal streams.  ``init`` is ``None`` (empty
     state), one row (broadcast) or an [N, K] matrix of running signatures.
     """
-    nv.require_device(device)
     tok, is64 = _as_tokens(tokens)
     off = np.ascontiguousarray(offsets, dtype=np.int64)
     if off.ndim != 1 or off.size < 1:
         raise ValueError("offsets must be a 1-D array of length n_docs + 1")
     n = off.size - 1
-    if n and (int(off[-1]) - int(off[0]) > tok.size or int(off[0]) < 0):
-        raise ValueError("offsets exceed the token array")
+    # the library indexes the token array with these offsets absolutely: validate all of them here
+    if n and (int(off[0]) < 0 or int(off[-1]) > tok.size or bool(np.any(np.diff(off) < 0))):
+        raise ValueError("offsets must be non-decreasing and lie inside the token array")
+    nv.require_device(device)
     h = nv.perm_handle(permutations, device)
     k = h.num_perm
     dt = np.uint64 if out_u64 else np.uint32
@@ -97,8 +98,14 @@ def bulk_signatures(tokens, offsets, permutations: np.ndarray, init: Optional[np
     return out
 
 
+def release_host_pipeline(device: int = -1) -> None:
+    """Free the streams and staging buffers ``bulk_signatures`` keeps per device between calls
+    (``dsk_release_host_pipeline``; -1 = all devices).  The next call re-creates them."""
+    nv.check(nv.load().dsk_release_host_pipeline(int(device)))
+
+
 def bulk_signatures_device(d_tokens, d_offsets, n_tokens: int, permutations: np.ndarray, d_out=None, d_init=None,
-                           init_stride: int = 0, kernel: str = "auto", stream: Optional[int] = None):
+                           init_stride: int = 0, kernel: str = "auto", stream: Optional[int] = None, workspace=None):
     """DEVICE buffers in (torch CUDA tensors: uint32/int32 or uint64/int64 tokens, int64 offsets),
     DEVICE [N, K] signature tensor out.  Asynchronous on ``stream`` (default: torch's current stream)."""
     import torch
@@ -115,11 +122,21 @@ def bulk_signatures_device(d_tokens, d_offsets, n_tokens: int, permutations: np.
     if stream is None:
         stream = torch.cuda.current_stream(d_tokens.device).cuda_stream
     with torch.cuda.device(dev):
-        nv.check(nv.load().dsk_minhash_bulk(h.handle, d_tokens.data_ptr() if n_tokens else None, is64,
-                                             d_offsets.data_ptr(), n, n_tokens,
-                                             d_init.data_ptr() if d_init is not None else None, init_stride,
-                                             int(d_init.element_size() == 8) if d_init is not None else 0,
-                                             d_out.data_ptr(), out64, KERNELS[kernel], stream))
+        # long documents (> 16384 tokens) are cut into pieces on the device: that needs a piece table, sized by the
+        # library and owned here (a torch tensor, kept alive until the launch was enqueued on a torch-known stream)
+        ws_bytes = int(nv.load().dsk_minhash_bulk_workspace_size(n, n_tokens)) if workspace is None else 0
+        if workspace is None and ws_bytes:
+            workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_tokens.device)
+        nv.check(nv.load().dsk_minhash_bulk_ws(h.handle, d_tokens.data_ptr() if n_tokens else None, is64,
+                                                d_offsets.data_ptr(), n, n_tokens,
+                                                d_init.data_ptr() if d_init is not None else None, init_stride,
+                                                int(d_init.element_size() == 8) if d_init is not None else 0,
+                                                d_out.data_ptr(), out64, KERNELS[kernel],
+                                                workspace.data_ptr() if workspace is not None else None,
+                                                workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                                                stream))
+        if workspace is not None:
+            workspace.record_stream(torch.cuda.ExternalStream(stream) if stream else torch.cuda.default_stream(d_tokens.device))
     return d_out
 
 
@@ -150,7 +167,7 @@ def _sha1_blob_device(blob, boff: np.ndarray, n: int, device: int = 0, out_u64: 
     with torch.cuda.device(device):
         nv.check(nv.load().dsk_sha1_tokens(d_bytes.data_ptr(), d_boff.data_ptr(), n, out.data_ptr(), int(out_u64),
                                             torch.cuda.current_stream(dev).cuda_stream))
-    return out[:n] if n >= 4 else out
+    return out[:n]     # (the allocation is padded to 4 elements; the result is not)
 
 
 def sha1_hash_tokens_device(flat_tokens, device: int = 0, out_u64: bool = False):

@@ -91,14 +91,27 @@ class WeightedMinHashGenerator:
         return st
 
     # -- sampling ----------------------------------------------------------------------------------
-    def _sample(self, X, device: int, many: bool):
-        """Device pass over [n, dim] weights -> ([n, sample_size, 2] int64 of (k, t), [n] bool all-zero rows)."""
+    def _sample(self, X, device: int, many: bool, device_log: bool = False):
+        """Device pass over [n, dim] weights -> ([n, sample_size, 2] int64 of (k, t), [n] bool all-zero rows).
+
+        For numpy input the logarithm is taken on the HOST with numpy's own float32 ``log`` -- the very call the
+        reference makes (weighted_minhash.py:150-152: zeros -> NaN, ``vlog = np.log(v)``) -- and the kernel gets
+        ``vlog`` (``DSK_WMH_INPUT_LOG``), so every step is bit-identical to the reference by construction.
+        ``device_log=True`` (and CUDA tensor input) lets the kernel take the logarithm itself: one pass less over
+        the data, values within 1 ulp of numpy's, the same (k, t) except on float near-ties."""
         import torch
+        flags = int(many)
         if isinstance(X, np.ndarray):
             X = np.ascontiguousarray(X, dtype=np.float32)
             if X.ndim != 2 or X.shape[1] != self.dim:
                 raise ValueError("Input dimension mismatch, expecting %d" % self.dim)
             h = self._handle(device)
+            if not device_log:
+                X = X.copy()
+                X[X == 0] = np.nan
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    X = np.log(X)
+                flags |= 2   # DSK_WMH_INPUT_LOG
             d_v = torch.from_numpy(X).cuda(device)
         else:
             if X.dim() != 2 or X.shape[1] != self.dim:
@@ -110,14 +123,14 @@ class WeightedMinHashGenerator:
         d_out = torch.empty((n, self.sample_size, 2), dtype=torch.int64, device=d_v.device)
         d_st = torch.empty((n,), dtype=torch.int32, device=d_v.device)
         with torch.cuda.device(device):
-            nv.check(nv.load().dsk_wmh_minhash(h, d_v.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), int(many),
+            nv.check(nv.load().dsk_wmh_minhash(h, d_v.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), flags,
                                                torch.cuda.current_stream(d_v.device).cuda_stream))
         return d_out.cpu().numpy(), d_st.cpu().numpy().astype(bool)
 
-    def minhash_batch(self, X, device: int = 0) -> np.ndarray:
+    def minhash_batch(self, X, device: int = 0, device_log: bool = False) -> np.ndarray:
         """[n, dim] weights -> [n, sample_size, 2] int64 of (k, t) -- row i equals
         ``self.minhash(X[i]).hashvalues``.  Raises ValueError if any row is all zeros."""
-        out, empty = self._sample(X, device, many=False)
+        out, empty = self._sample(X, device, many=False, device_log=device_log)
         if empty.any():
             raise ValueError("Input is all zeros")
         return out

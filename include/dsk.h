@@ -93,6 +93,20 @@ DSK_API int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int tok
                      const void *d_init, int64_t init_stride, int init_is_u64,
                      void *d_out, int out_is_u64, int flags, void *stream);
 
+/* Same, with a caller-provided device workspace that lets the library cut LONG documents (> 16384 tokens) into pieces
+ * of 4096 tokens on the device: the warp that meets such a document stores the row's initial value and appends the
+ * pieces to a table in the workspace; a second launch spreads the pieces over all warps and min-merges their partial
+ * signatures into the row (atomicMin; MinHash.merge is the combine rule, minhash.py:337-359).  Without a workspace
+ * (dsk_minhash_bulk) one warp handles a whole document, whatever its length.  d_workspace: 16-byte aligned,
+ * >= dsk_minhash_bulk_workspace_size(n_docs, n_tokens) bytes (0 when no document can be long), contents undefined on
+ * entry and on return, owned by the caller, in use until the launch has finished on `stream`.
+ * The reference's own GPU benchmark shape is one 50 000-token update_batch (benchmark/sketches/minhash_gpu_benchmark.py:42-48). */
+DSK_API size_t dsk_minhash_bulk_workspace_size(int64_t n_docs, int64_t n_tokens);
+DSK_API int dsk_minhash_bulk_ws(const dsk_perm *perm, const void *d_tokens, int token_is_u64,
+                        const int64_t *d_offsets, int64_t n_docs, int64_t n_tokens,
+                        const void *d_init, int64_t init_stride, int init_is_u64,
+                        void *d_out, int out_is_u64, int flags, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Fused signature build + all-gather (multi-GPU): like dsk_minhash_bulk, but each signature row
  * is stored straight into row (row_offset + i) of the FULL [N_total, num_perm] matrix of every
  * rank: h_peer_out[0..n_peers) are device pointers to those matrices (this rank's own buffer
@@ -113,6 +127,14 @@ DSK_API int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, in
                           const int64_t *h_offsets, int64_t n_docs,
                           const void *h_init, int64_t init_stride, int init_is_u64,
                           void *h_out, int out_is_u64, int flags);
+
+/* Ownership (see INTEGRATION.md "What the library allocates"): every d_ / h_ buffer above is the caller's.  The
+ * library itself holds (a) per dsk_perm handle: the permutation table, 16 KB of work counters and 64 events, freed by
+ * dsk_perm_destroy; (b) per device, created by the first dsk_minhash_bulk_host call and grown on demand: three
+ * streams and three slots of device + pinned staging buffers sized to the largest slice seen (<= 16 Mi tokens,
+ * <= 128 Ki documents per slice).  dsk_release_host_pipeline frees (b) for `device` (-1 = every device); the next
+ * host-buffer call re-creates it.  Not to be called concurrently with dsk_minhash_bulk_host on the same device. */
+DSK_API int dsk_release_host_pipeline(int device);
 
 /* Element-wise min of two signature matrices (MinHash.merge / union,
  * datasketch/minhash.py:359, :453; LeanMinHash.union lean_minhash.py:249). */
@@ -166,9 +188,13 @@ DSK_API int dsk_bloom_query(const uint32_t *d_sig, int64_t n, int num_perm, int 
  *   d_out    [n, sample_size, 2] int64: (k, int(t_k)) per sample (:158)
  *   d_status [n] int32: 1 where the input row is all zeros (reference: ValueError, :149-150)
  *   flags    DSK_WMH_MINHASH (0), or DSK_WMH_MINHASH_MANY: the float32 operation order of the
- *            reference's experimental minhash_many (:221-224; an all-zero row is None there, :241-245) */
+ *            reference's experimental minhash_many (:221-224; an all-zero row is None there, :241-245)
+ *            | DSK_WMH_INPUT_LOG: d_v holds ln(weight) already (float32, NaN where the weight is zero) -- the host
+ *            layer passes numpy's own float32 log (:152), which makes every step bit-identical to the reference;
+ *            without it the kernel takes a correctly rounded log itself (<= 1 ulp from numpy's) */
 #define DSK_WMH_MINHASH 0
 #define DSK_WMH_MINHASH_MANY 1
+#define DSK_WMH_INPUT_LOG 2
 typedef struct dsk_wmh dsk_wmh;
 DSK_API int dsk_wmh_create(const float *h_rs, const float *h_ln_cs, const float *h_betas, int sample_size, int dim,
                            int device, dsk_wmh **out);

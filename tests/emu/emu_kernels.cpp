@@ -56,6 +56,39 @@ extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int6
     return dsk::launch_minhash_bulk(prm, mode, token_is_u64, grid_x, nullptr);
 }
 
+// the signature kernel with the long-document piece table (thresholds chosen by the test, e.g. 100 / 40 tokens)
+extern "C" int emu_minhash_sig_long(const uint32_t *tokens, const int64_t *offsets, int64_t n_docs, const uint64_t *a,
+                                    const uint64_t *b, int k, const void *init, int64_t init_stride, int init_is_u64,
+                                    void *out, int out_is_u64, int docs_per_unit, int grid_x, int64_t long_doc_tokens,
+                                    int piece_tokens, long long *n_pieces_out) {
+    const int kpad = (k + 255) / 256 * 256;
+    std::vector<uint32_t> tab((size_t)5 * kpad);
+    for (int i = 0; i < kpad; ++i) {
+        const int s = i % k;
+        tab[i] = (uint32_t)a[s]; tab[kpad + i] = (uint32_t)(a[s] >> 32);
+        tab[2 * kpad + i] = (uint32_t)b[s]; tab[3 * kpad + i] = (uint32_t)(b[s] >> 32);
+        tab[4 * kpad + i] = (uint32_t)b[s] + 7u;
+    }
+    std::vector<unsigned> counters(64, 0u);
+    const int64_t n_tokens = offsets[n_docs];
+    const size_t cap = (size_t)(n_tokens / piece_tokens + n_tokens / long_doc_tokens + 2);
+    std::vector<unsigned char> ws(dsk::kPieceHdrBytes + cap * sizeof(dsk::PieceDesc) + 64, 0xCD);   // contents undefined on entry
+    unsigned char *wsp = ws.data() + (16 - (reinterpret_cast<uintptr_t>(ws.data()) & 15)) % 16;
+    dsk::BulkParams prm{};
+    prm.tokens = tokens; prm.offsets = offsets; prm.n_docs = n_docs; prm.n_tokens = n_tokens;
+    prm.a_lo = tab.data(); prm.a_hi = tab.data() + kpad; prm.b_lo = tab.data() + 2 * kpad; prm.b_hi = tab.data() + 3 * kpad;
+    prm.b_lo7 = tab.data() + 4 * kpad;
+    prm.k = k; prm.init = init; prm.init_stride = init_stride; prm.init_is_u64 = init_is_u64;
+    prm.out = out; prm.out_is_u64 = out_is_u64; prm.work_counter = counters.data();
+    prm.docs_per_unit = docs_per_unit;
+    prm.long_doc_tokens = long_doc_tokens; prm.piece_tokens = piece_tokens;
+    prm.piece_hdr = reinterpret_cast<unsigned *>(wsp);
+    prm.pieces = reinterpret_cast<dsk::PieceDesc *>(wsp + dsk::kPieceHdrBytes);
+    const int rc = dsk::launch_minhash_sig(prm, grid_x, nullptr);
+    if (n_pieces_out) *n_pieces_out = *reinterpret_cast<unsigned *>(wsp);
+    return rc;
+}
+
 // path counters of minhash_sig_kernel (read-and-reset): in place / copied / deduplicated sub-pieces, tokens removed, flagged perms
 extern "C" void emu_sig_stats(long long *out5) {
     for (int i = 0; i < dsk::STAT_COUNT; ++i) out5[i] = dsk::g_sig_stat[i].exchange(0);
@@ -154,7 +187,8 @@ extern "C" int emu_hash_tokens(const uint8_t *bytes, const int64_t *off, int64_t
 }
 // rs / ln_cs / betas: [ss][dim] as the generator holds them; transposed to [dim][ss_pad] like dsk_wmh_create
 extern "C" int emu_wmh(const float *rs, const float *ln_cs, const float *betas, int ss, int dim, const float *v, int64_t n,
-                       int64_t *out, int32_t *status, int many) {
+                       int64_t *out, int32_t *status, int flags) {
+    const int many = flags & 1, input_log = (flags >> 1) & 1;   // DSK_WMH_MINHASH_MANY | DSK_WMH_INPUT_LOG
     const int ss_pad = (ss + 31) / 32 * 32;
     std::vector<float> par((size_t)3 * dim * ss_pad);
     const float *src[3] = {rs, ln_cs, betas};
@@ -162,5 +196,5 @@ extern "C" int emu_wmh(const float *rs, const float *ln_cs, const float *betas, 
         if (dsk::launch_wmh_transpose(src[i], ss, dim, ss_pad, par.data() + (size_t)i * dim * ss_pad, nullptr)) return -1;
     const size_t plane = (size_t)dim * ss_pad;
     return dsk::launch_wmh(par.data(), par.data() + plane, par.data() + 2 * plane, ss, ss_pad, dim, v, n, out, status, many,
-                           2, nullptr);
+                           input_log, 2, nullptr);
 }

@@ -251,3 +251,68 @@ def test_remaining_entry_points_through_the_c_abi(emu_lib, golden):
     assert not stv.any() and np.array_equal(kt, w["tiny_out"])
     assert lib.dsk_wmh_minhash(gen, ptr(V), I64(len(V)), ptr(kt), ptr(stv), 5, None) != 0      # unknown flags
     lib.dsk_wmh_destroy(gen)
+
+
+def test_release_host_pipeline_and_counter_leases(emu_lib, monkeypatch):
+    """dsk_release_host_pipeline frees the per-device staging (the next host call re-creates it and still gives the
+    oracle's rows); more launches than counter sets (64) through one permutation handle stay correct."""
+    lib = emu_lib
+    monkeypatch.setenv("DSK_SLICE_TOKENS", "4096")
+    rs = np.random.RandomState(2)
+    lens = rs.randint(0, 120, size=40)
+    off = np.zeros(41, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    perms = o.init_permutations(64, 1)
+    a, b = np.ascontiguousarray(perms[0]), np.ascontiguousarray(perms[1])
+    h = ctypes.c_void_p()
+    assert lib.dsk_perm_create(a.ctypes.data, b.ctypes.data, 64, 0, ctypes.byref(h)) == 0
+    want = oc.minhash_bulk_u32tok(tok, off, perms)
+    out = np.zeros((40, 64), dtype=np.uint32)
+    for round_ in range(3):
+        out[:] = 0
+        assert lib.dsk_minhash_bulk_host(h, tok.ctypes.data, 0, off.ctypes.data, 40, None, 0, 0, out.ctypes.data, 0, 0) == 0
+        assert np.array_equal(out, want)
+        assert lib.dsk_release_host_pipeline(0 if round_ else -1) == 0
+    assert lib.dsk_release_host_pipeline(99) != 0
+    tok16 = np.zeros(len(tok) + 4, dtype=np.uint32)
+    tok16[:len(tok)] = tok
+    for i in range(70):                                   # > 64 launches: counter sets are leased round-robin
+        out[:] = 0
+        assert lib.dsk_minhash_bulk(h, tok16.ctypes.data, 0, off.ctypes.data, 40, len(tok), None, 0, 0, out.ctypes.data, 0, 0, None) == 0
+        if i % 23 == 0:
+            assert np.array_equal(out, want)
+    assert np.array_equal(out, want)
+    lib.dsk_perm_destroy(h)
+
+
+def test_minhash_bulk_ws_cuts_long_documents(emu_lib):
+    """dsk_minhash_bulk_ws with the library-sized workspace: a 60 000-token and a 20 000-token document between short ones
+    (the reference's GPU benchmark shape is one 50 000-token update_batch); workspace size / alignment validation."""
+    lib = emu_lib
+    rs = np.random.RandomState(9)
+    lens = np.array([50, 60_000, 0, 300, 20_000, 16_384, 9], dtype=np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    nt = int(off[-1])
+    tok = np.zeros(nt + 4, dtype=np.uint32)
+    tok[:nt] = rs.randint(0, 1 << 32, size=nt, dtype=np.uint64).astype(np.uint32)
+    perms = o.init_permutations(32, 1)
+    a, b = np.ascontiguousarray(perms[0]), np.ascontiguousarray(perms[1])
+    h = ctypes.c_void_p()
+    assert lib.dsk_perm_create(a.ctypes.data, b.ctypes.data, 32, 0, ctypes.byref(h)) == 0
+    want = oc.minhash_bulk_u32tok(tok[:nt], off, perms)
+    need = lib.dsk_minhash_bulk_workspace_size(len(lens), nt)
+    assert need > 0 and lib.dsk_minhash_bulk_workspace_size(5, 16_384) == 0
+    ws = np.full(need // 8 + 4, 0xAB, dtype=np.uint64)
+    out = np.zeros((len(lens), 32), dtype=np.uint32)
+    args = (h, tok.ctypes.data, 0, off.ctypes.data, len(lens), nt, None, 0, 0, out.ctypes.data, 0, 0)
+    assert lib.dsk_minhash_bulk_ws(*args, ws.ctypes.data, need, None) == 0
+    assert np.array_equal(out, want)
+    assert int(ws.view(np.uint32)[0]) == 15 + 5                      # pieces of the two long documents
+    out[:] = 0
+    assert lib.dsk_minhash_bulk_ws(*args, None, 0, None) == 0        # no workspace: one warp per document, same rows
+    assert np.array_equal(out, want)
+    assert lib.dsk_minhash_bulk_ws(*args, ws.ctypes.data, need - 1, None) != 0 and b"workspace" in lib.dsk_last_error()
+    assert lib.dsk_minhash_bulk_ws(*args, ws.ctypes.data + 4, need, None) != 0
+    lib.dsk_perm_destroy(h)

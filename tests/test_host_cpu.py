@@ -156,3 +156,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("the oracle", ""), os.path.join(dp, f)
+
+
+def test_bulk_signatures_validates_every_offset(dsk):
+    """engine.bulk_signatures checks the offsets BEFORE the library indexes host memory with them:
+    offsets[0] > 0 past the end, a decreasing interior offset, a negative start."""
+    P = dsk.minhash._make_permutations(16, 1)
+    tok = np.arange(10, dtype=np.uint32)
+    for off in ([5, 13], [0, 6, 4, 10], [-1, 3], [0, 11]):
+        with pytest.raises(ValueError):
+            dsk.engine.bulk_signatures(tok, np.array(off, dtype=np.int64), P)

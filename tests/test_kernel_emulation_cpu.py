@@ -187,6 +187,38 @@ def test_deduplication_switches_on_and_off(emu):
     assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=7, grid_x=2), want)
 
 
+@pytest.mark.parametrize("k", [128, 300])
+def test_long_documents_are_cut_into_pieces_on_the_device(emu, k):
+    """signature_kernel.cu piece mode (thresholds shrunk to 100 / 40 tokens so the emulation stays small): the warp that
+    meets a long document stores the row's initial value and appends pieces; the second launch min-merges them with
+    atomicMin.  Mixed with short / empty documents, running-state merge, u64 output, K sliced over blockIdx.y (k = 300)."""
+    lib = emu.lib
+    rs = np.random.RandomState(k)
+    lens = np.array([30, 250, 0, 101, 100, 1000, 7, 99, 481, 40, 3000, 12], dtype=np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]) + 3, dtype=np.uint64).astype(np.uint32)[:int(off[-1])]
+    tok[off[5]:off[5] + 500] = tok[off[5] + 500:off[5] + 1000]          # repeats inside a long document
+    perms = o.init_permutations(k, 4)
+    a, b = np.ascontiguousarray(perms[0]), np.ascontiguousarray(perms[1])
+    want = oc.minhash_bulk_u32tok(tok, off, perms)
+    n = len(lens)
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.emu_minhash_sig_long.argtypes = [vp, vp, i64, vp, vp, ci, vp, i64, ci, vp, ci, ci, ci, i64, ci, vp]
+    npieces = ctypes.c_longlong(0)
+    for dpu, gx in ((3, 1), (1, 2), (32, 2)):
+        out = np.zeros((n, k), dtype=np.uint32)
+        assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, None, 0, 0,
+                                        out.ctypes.data, 0, dpu, gx, 100, 40, ctypes.byref(npieces)) == 0
+        assert np.array_equal(out, want), (dpu, gx)
+        assert npieces.value == sum(-(-int(x) // 40) for x in lens if x > 100)      # 250, 101, 1000, 481, 3000
+    init = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64)
+    out64 = np.zeros((n, k), dtype=np.uint64)
+    assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, init.ctypes.data, k, 1,
+                                    out64.ctypes.data, 1, 2, 2, 100, 40, None) == 0
+    assert np.array_equal(out64, np.minimum(want.astype(np.uint64), init))
+
+
 def test_u64_tokens_init_merge_and_u64_output(emu):
     rs = np.random.RandomState(4)
     tok32, off = _ragged(rs, 30, 90)

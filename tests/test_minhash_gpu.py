@@ -260,6 +260,50 @@ def test_long_documents_are_split_and_merged(dsk, kernel):
     assert np.array_equal(m.hashvalues, oc.minhash_bulk_u32tok(tok[:50_000], np.array([0, 50_000]), P)[0].astype(np.uint64))
 
 
+def test_long_documents_on_the_device_buffer_entry(dsk):
+    """dsk_minhash_bulk_ws through engine.bulk_signatures_device: long documents are cut into pieces ON THE DEVICE
+    (signature_kernel.cu piece mode, caller-owned workspace) -- one 2.5 M-token document, the reference's 50 000-token
+    benchmark shape, repeats inside a long document, long documents at the batch's ends; u64 output + running state."""
+    import torch
+    rs = np.random.RandomState(33)
+    lens = [60_000, 5000, 0, 17, 16_384, 16_385, 50_000, 3, 2_500_000, 129, 20_000]
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 2 ** 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    tok[off[6]:off[6] + 25_000] = tok[off[6] + 25_000:off[7]]          # a long document made of repeats
+    for k in (128, 256, 300):
+        P = o.init_permutations(k, 1)
+        want = oc.minhash_bulk_u32tok(tok, off, P)
+        d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+        d_off = torch.from_numpy(off).cuda()
+        got = dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), k
+    init = rs.randint(0, 2 ** 32, size=(len(lens), 300), dtype=np.uint64)
+    d_init = torch.from_numpy(init.view(np.int64)).cuda()
+    d_out = torch.empty((len(lens), 300), dtype=torch.int64, device="cuda")
+    dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P, d_out=d_out, d_init=d_init, init_stride=300)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), np.minimum(init, want.astype(np.uint64)))
+    # timing contract (VERDICT r1 item 7): one 2.5 M-token document within 1.5x of the same tokens as 1000 documents
+    one = torch.from_numpy(tok[off[8]:off[9]].view(np.int32).copy()).cuda()
+    P = o.init_permutations(128, 1)
+    off1 = torch.tensor([0, 2_500_000], dtype=torch.int64, device="cuda")
+    offk = torch.arange(0, 2_500_001, 2500, dtype=torch.int64, device="cuda")
+
+    def ms(o_):
+        for _ in range(2):
+            dsk.engine.bulk_signatures_device(one, o_, 2_500_000, P)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dsk.engine.bulk_signatures_device(one, o_, 2_500_000, P)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+    t_one, t_many = ms(off1), ms(offk)
+    assert t_one < 1.5 * t_many + 0.05, (t_one, t_many)
+
+
 def test_full_size_c2_properties(dsk):
     """BASELINE.json configs[1] at full size (1M docs x 256 tokens, K=128): size-independent properties
     plus a sampled comparison with the C oracle."""

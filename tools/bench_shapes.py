@@ -71,6 +71,9 @@ run("short_aligned_4Mx64", np.full(4_000_000, 64), 128)
 run("short_ragged_4M_16to112", rs.randint(16, 113, size=4_000_000), 128)
 run("long_20k_x12800", np.full(20_000, 12_800), 128)
 run("long_ragged_40k_2kto10k", rs.randint(2_000, 10_001, size=40_000), 128)
+run("one_doc_2.5M_tokens", np.array([2_500_000]), 128, iters=10)
+run("same_tokens_as_1000_docs", np.full(1000, 2500), 128, iters=10)
+run("reference_bench_shape_1x50k", np.array([50_000]), 128, iters=20)
 run("k256_2Mx128", np.full(2_000_000, 128), 256)
 run("k64_2Mx256", np.full(2_000_000, 256), 64)
 for share in (0.01, 0.1, 0.5):
