@@ -136,17 +136,22 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
         int64_t c_wait = c_next;                                // next chunk to wait for
         const int64_t c_last = (tok_hi - 1) >> kChunkShift;     // last chunk this unit touches (if it has tokens)
 
+        // consume the completions of copies that were issued for chunks < upto but never needed (skipped tokens): every
+        // issued copy must be waited for exactly once, or the slot's phase parity goes out of step
+        auto drain = [&](int64_t upto) {
+            while (c_wait < upto && c_wait < c_next) {
+                const int slot = (int)(c_wait & (kRingSlots - 1));
+                mbar_wait(&bar[slot], (par_mask >> slot) & 1u);
+                par_mask ^= 1u << slot;
+                ++c_wait;
+            }
+        };
         // make tokens [s, e) resident in the ring: chunk c lives in slot c & 3.  Chunks before s's chunk are dead (every
         // earlier sub-piece is finished), so up to three chunks beyond it can be in flight.
         auto ensure = [&](int64_t s, int64_t e) {
             const int64_t cf = s >> kChunkShift, cl = (e - 1) >> kChunkShift;
             if (c_wait < cf) {   // tokens were skipped (a deferred long document): drain what is in flight, jump ahead
-                while (c_wait < cf && c_wait < c_next) {
-                    const int slot = (int)(c_wait & (kRingSlots - 1));
-                    mbar_wait(&bar[slot], (par_mask >> slot) & 1u);
-                    par_mask ^= 1u << slot;
-                    ++c_wait;
-                }
+                drain(cf);
                 c_wait = cf;
                 if (c_next < cf) c_next = cf;
             }
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
             }
             start = end;
         }
+        drain(c_next);   // (only a unit that ends in a deferred document has copies left in flight)
     }  // units
 }
 
