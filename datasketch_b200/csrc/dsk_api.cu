@@ -342,7 +342,7 @@ int dsk_minhash_bulk_ws(const dsk_perm *perm, const void *d_tokens, int token_is
     prm.peer_row_offset = 0;
     if (d_workspace && minhash_sig_workspace_bytes(n_tokens) > 0) {   // long documents are cut into pieces on the device
         prm.long_doc_tokens = kLongDocTokensApi;
-        prm.piece_tokens = kPieceTokensApi;
+        prm.piece_shift = kPieceShiftApi;
         prm.piece_hdr = static_cast<unsigned *>(d_workspace);
         prm.pieces = reinterpret_cast<PieceDesc *>(static_cast<char *>(d_workspace) + kPieceHdrBytes);
     }

@@ -57,17 +57,17 @@ struct BulkParams {
     int64_t peer_row_offset;
     void *peer_out[8];
     // long documents (signature_kernel.cu): a document longer than long_doc_tokens is not processed by the warp that
-    // meets it; the warp stores the row's initial value and appends ceil(len / piece_tokens) PieceDesc entries, which a
+    // meets it; the warp stores the row's initial value and appends ceil(len / 2^piece_shift) PieceDesc entries, which a
     // second launch of the kernel in piece mode spreads over all warps and min-merges into the row with atomicMin.
     int64_t long_doc_tokens;    // 0 = never defer
-    int piece_tokens;
+    int piece_shift;            // log2 of the piece length in tokens
     unsigned *piece_hdr;        // [0] = pieces appended so far; [64 + K-slice] = work counters of the piece-mode launch
-    struct PieceDesc *pieces;   // capacity guaranteed by the launcher: n_tokens / piece_tokens + n_tokens / long_doc_tokens + 1
+    struct PieceDesc *pieces;   // capacity guaranteed by the caller: n_tokens / 2^piece_shift + n_tokens / long_doc_tokens + 2
 };
 struct PieceDesc { int64_t row, start, end, reserved; };
 constexpr int kPieceHdrBytes = 512;
-constexpr int64_t kLongDocTokensApi = 16384;   // documents longer than this are cut into pieces of kPieceTokensApi tokens
-constexpr int kPieceTokensApi = 4096;
+constexpr int64_t kLongDocTokensApi = 4096;   // documents longer than this are cut into pieces of 2^kPieceShiftApi tokens
+constexpr int kPieceShiftApi = 10;
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
 cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s);   // signature_kernel.cu (two-phase)
@@ -104,7 +104,7 @@ struct LshDev {
     uint32_t *sig;        // [cap_docs][k] copies of the inserted signatures (tuple verification)
     uint64_t *slot_key;   // [b][cap_slots]
     int32_t *slot_head;   // [b][cap_slots]  most recently inserted doc of the bucket, -1 = none
-    int32_t *next;        // [b][cap_docs]   next doc in the same bucket, -1 = end
+    int32_t *next;        // [cap_docs][b]   next doc in the same bucket of that band, -1 = end
     int64_t cap_docs, cap_slots;  // cap_slots is a power of two >= 2 * cap_docs
     int k, b, r;
 };

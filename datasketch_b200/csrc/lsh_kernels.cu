@@ -35,27 +35,41 @@ __device__ __forceinline__ bool tuple_eq(const uint32_t *a, const uint32_t *b, i
     return eq;
 }
 
-// thread <-> (new document, band)
+// warp <-> new document.  The row is read ONCE with coalesced loads: each value goes to the index's own copy of the
+// signatures (candidates are verified on the r-tuples themselves) and to a shared-memory line, from which lane j takes
+// band j's r-tuple for the fingerprint.  DRAM traffic per document: 4K in, 4K out (the copy), b x 16 bytes of table /
+// chain updates -- the separate device-to-device copy and the b uncoalesced re-reads of the row of the first version
+// (thread <-> (document, band)) are gone.  next[] is laid out [doc][band], so a document's b links are one coalesced store.
 __global__ void __launch_bounds__(256) lsh_insert_kernel(const LshDev ix, const uint32_t *__restrict__ new_sig,
                                                          int64_t doc0, int64_t n_new) {
-    const int64_t total = n_new * ix.b, stride = (int64_t)gridDim.x * blockDim.x;
+    DSK_DYNAMIC_SMEM_T(uint32_t, s_rows, 16);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t *srow = s_rows + (size_t)w * ix.k;
     const uint64_t mask = (uint64_t)ix.cap_slots - 1;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int64_t i = e / ix.b;
-        const int band = (int)(e - i * ix.b);
+    for (int64_t i = (int64_t)blockIdx.x * nw + w; i < n_new; i += (int64_t)gridDim.x * nw) {
         const int64_t doc = doc0 + i;
         const uint32_t *row = new_sig + i * ix.k;
-        const uint64_t fp = band_fp(row + (int64_t)band * ix.r, ix.r, band);
-        uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
-        uint64_t slot = lsh_mix64(fp) & mask;
-        while (true) {
-            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(keys + slot),
-                                                      (unsigned long long)kEmptyKey, (unsigned long long)fp);
-            if (prev == kEmptyKey || prev == fp) break;
-            slot = (slot + 1) & mask;
+        uint32_t *keep = ix.sig + doc * ix.k;
+        __syncwarp();
+        for (int c = lane; c < ix.k; c += 32) {
+            const uint32_t v = __ldg(row + c);
+            srow[c] = v;
+            keep[c] = v;
         }
-        const int32_t old = atomicExch(ix.slot_head + (int64_t)band * ix.cap_slots + slot, (int32_t)doc);
-        ix.next[(int64_t)band * ix.cap_docs + doc] = old;
+        __syncwarp();
+        for (int band = lane; band < ix.b; band += 32) {
+            const uint64_t fp = band_fp(srow + band * ix.r, ix.r, band);
+            uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
+            uint64_t slot = lsh_mix64(fp) & mask;
+            while (true) {
+                const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(keys + slot),
+                                                          (unsigned long long)kEmptyKey, (unsigned long long)fp);
+                if (prev == kEmptyKey || prev == fp) break;
+                slot = (slot + 1) & mask;
+            }
+            const int32_t old = atomicExch(ix.slot_head + (int64_t)band * ix.cap_slots + slot, (int32_t)doc);
+            ix.next[doc * ix.b + band] = old;
+        }
     }
 }
 
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(256) lsh_query_kernel(const LshDev ix, const u
                                 }
                             }
                         }
-                        d = ix.next[(int64_t)band * ix.cap_docs + d];
+                        d = ix.next[(int64_t)d * ix.b + band];
                     }
                 }
                 if (pass == 0) {
@@ -163,14 +177,14 @@ __global__ void __launch_bounds__(kScanBlock) scan_add_kernel(int64_t *out, int6
 cudaError_t launch_lsh_insert(const LshDev &ix, const uint32_t *new_sig, int64_t doc0, int64_t n_new, int sm_count,
                               cudaStream_t s) {
     if (n_new <= 0) return cudaSuccess;
-    // the index keeps its own copy of the rows: candidates are verified on the r-tuples themselves
-    cudaError_t e = cudaMemcpyAsync(ix.sig + doc0 * ix.k, new_sig, (size_t)n_new * ix.k * sizeof(uint32_t),
-                                    cudaMemcpyDeviceToDevice, s);
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * ix.k * 4 > 64 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * ix.k * 4;
+    cudaError_t e = cudaFuncSetAttribute(lsh_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int64_t total = n_new * ix.b;
-    int64_t grid = (total + 255) / 256;
-    if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
-    DSK_LAUNCH(lsh_insert_kernel, (unsigned)grid, 256, 0, s, ix, new_sig, doc0, n_new);
+    int64_t grid = (n_new + warps - 1) / warps;
+    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+    DSK_LAUNCH(lsh_insert_kernel, (unsigned)grid, warps * 32, smem, s, ix, new_sig, doc0, n_new);
     return cudaGetLastError();
 }
 

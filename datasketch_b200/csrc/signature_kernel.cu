@@ -72,6 +72,26 @@ __device__ __forceinline__ void load_block16(const uint32_t *src, uint32_t (&t)[
     }
 }
 
+// A long document's pieces (2^piece_shift tokens each) go to the table the second launch works through.
+#ifndef DSK_EMU
+__device__ __forceinline__
+#else
+static inline
+#endif
+void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int64_t row, int64_t start, int64_t end, int lane) {
+    const int64_t step = (int64_t)1 << piece_shift;
+    const int64_t np = (end - start + step - 1) >> piece_shift;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(piece_hdr, (unsigned)np);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (int64_t q = lane; q < np; q += 32) {
+        PieceDesc pd;
+        pd.row = row; pd.start = start + (q << piece_shift);
+        pd.end = min(end, pd.start + step); pd.reserved = 0;
+        pieces[base + q] = pd;
+    }
+}
+
 template <int P, int OCC, bool PIECES>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
     __shared__ __align__(128) uint32_t s_ring[kSigWarps][kRingTok];
@@ -202,18 +222,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
             bool defer = false;
             if constexpr (!PIECES) {
                 defer = prm.long_doc_tokens > 0 && end - start > prm.long_doc_tokens;
-                if (defer && blockIdx.y == 0) {
-                    const int64_t np = (end - start + prm.piece_tokens - 1) / prm.piece_tokens;
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(prm.piece_hdr, (unsigned)np);
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    for (int64_t q = lane; q < np; q += 32) {
-                        PieceDesc pd;
-                        pd.row = d; pd.start = start + q * prm.piece_tokens;
-                        pd.end = min(end, pd.start + (int64_t)prm.piece_tokens); pd.reserved = 0;
-                        prm.pieces[base + q] = pd;
-                    }
-                }
+                if (defer && blockIdx.y == 0) append_pieces(prm.piece_hdr, prm.pieces, prm.piece_shift, d, start, end, lane);
             }
 
             for (int64_t s = start; s < (defer ? start : end); s += kSubTok) {
@@ -476,7 +485,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
 }
 
 constexpr int64_t kLongDocTokens = kLongDocTokensApi;
-constexpr int kPieceTokens = kPieceTokensApi;
+constexpr int kPieceTokens = 1 << kPieceShiftApi;
 
 // bytes of the piece table a launch over n_tokens tokens can need (0: no document can be long enough)
 size_t minhash_sig_workspace_bytes(int64_t n_tokens) {

@@ -93,8 +93,8 @@ DSK_API int dsk_minhash_bulk(const dsk_perm *perm, const void *d_tokens, int tok
                      const void *d_init, int64_t init_stride, int init_is_u64,
                      void *d_out, int out_is_u64, int flags, void *stream);
 
-/* Same, with a caller-provided device workspace that lets the library cut LONG documents (> 16384 tokens) into pieces
- * of 4096 tokens on the device: the warp that meets such a document stores the row's initial value and appends the
+/* Same, with a caller-provided device workspace that lets the library cut LONG documents (> 4096 tokens) into pieces
+ * of 1024 tokens on the device: the warp that meets such a document stores the row's initial value and appends the
  * pieces to a table in the workspace; a second launch spreads the pieces over all warps and min-merges their partial
  * signatures into the row (atomicMin; MinHash.merge is the combine rule, minhash.py:337-359).  Without a workspace
  * (dsk_minhash_bulk) one warp handles a whole document, whatever its length.  d_workspace: 16-byte aligned,

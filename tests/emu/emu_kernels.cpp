@@ -56,11 +56,11 @@ extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int6
     return dsk::launch_minhash_bulk(prm, mode, token_is_u64, grid_x, nullptr);
 }
 
-// the signature kernel with the long-document piece table (thresholds chosen by the test, e.g. 100 / 40 tokens)
+// the signature kernel with the long-document piece table (thresholds chosen by the test, e.g. 100 / 32 tokens)
 extern "C" int emu_minhash_sig_long(const uint32_t *tokens, const int64_t *offsets, int64_t n_docs, const uint64_t *a,
                                     const uint64_t *b, int k, const void *init, int64_t init_stride, int init_is_u64,
                                     void *out, int out_is_u64, int docs_per_unit, int grid_x, int64_t long_doc_tokens,
-                                    int piece_tokens, long long *n_pieces_out) {
+                                    int piece_shift, long long *n_pieces_out) {
     const int kpad = (k + 255) / 256 * 256;
     std::vector<uint32_t> tab((size_t)5 * kpad);
     for (int i = 0; i < kpad; ++i) {
@@ -71,7 +71,7 @@ extern "C" int emu_minhash_sig_long(const uint32_t *tokens, const int64_t *offse
     }
     std::vector<unsigned> counters(64, 0u);
     const int64_t n_tokens = offsets[n_docs];
-    const size_t cap = (size_t)(n_tokens / piece_tokens + n_tokens / long_doc_tokens + 2);
+    const size_t cap = (size_t)((n_tokens >> piece_shift) + n_tokens / long_doc_tokens + 2);
     std::vector<unsigned char> ws(dsk::kPieceHdrBytes + cap * sizeof(dsk::PieceDesc) + 64, 0xCD);   // contents undefined on entry
     unsigned char *wsp = ws.data() + (16 - (reinterpret_cast<uintptr_t>(ws.data()) & 15)) % 16;
     dsk::BulkParams prm{};
@@ -81,7 +81,7 @@ extern "C" int emu_minhash_sig_long(const uint32_t *tokens, const int64_t *offse
     prm.k = k; prm.init = init; prm.init_stride = init_stride; prm.init_is_u64 = init_is_u64;
     prm.out = out; prm.out_is_u64 = out_is_u64; prm.work_counter = counters.data();
     prm.docs_per_unit = docs_per_unit;
-    prm.long_doc_tokens = long_doc_tokens; prm.piece_tokens = piece_tokens;
+    prm.long_doc_tokens = long_doc_tokens; prm.piece_shift = piece_shift;
     prm.piece_hdr = reinterpret_cast<unsigned *>(wsp);
     prm.pieces = reinterpret_cast<dsk::PieceDesc *>(wsp + dsk::kPieceHdrBytes);
     const int rc = dsk::launch_minhash_sig(prm, grid_x, nullptr);

@@ -291,7 +291,7 @@ def test_minhash_bulk_ws_cuts_long_documents(emu_lib):
     (the reference's GPU benchmark shape is one 50 000-token update_batch); workspace size / alignment validation."""
     lib = emu_lib
     rs = np.random.RandomState(9)
-    lens = np.array([50, 60_000, 0, 300, 20_000, 16_384, 9], dtype=np.int64)
+    lens = np.array([50, 60_000, 0, 300, 20_000, 4096, 9], dtype=np.int64)
     off = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     nt = int(off[-1])
@@ -303,13 +303,13 @@ def test_minhash_bulk_ws_cuts_long_documents(emu_lib):
     assert lib.dsk_perm_create(a.ctypes.data, b.ctypes.data, 32, 0, ctypes.byref(h)) == 0
     want = oc.minhash_bulk_u32tok(tok[:nt], off, perms)
     need = lib.dsk_minhash_bulk_workspace_size(len(lens), nt)
-    assert need > 0 and lib.dsk_minhash_bulk_workspace_size(5, 16_384) == 0
+    assert need > 0 and lib.dsk_minhash_bulk_workspace_size(5, 4096) == 0
     ws = np.full(need // 8 + 4, 0xAB, dtype=np.uint64)
     out = np.zeros((len(lens), 32), dtype=np.uint32)
     args = (h, tok.ctypes.data, 0, off.ctypes.data, len(lens), nt, None, 0, 0, out.ctypes.data, 0, 0)
     assert lib.dsk_minhash_bulk_ws(*args, ws.ctypes.data, need, None) == 0
     assert np.array_equal(out, want)
-    assert int(ws.view(np.uint32)[0]) == 15 + 5                      # pieces of the two long documents
+    assert int(ws.view(np.uint32)[0]) == 59 + 20                     # 1024-token pieces of the two long documents
     out[:] = 0
     assert lib.dsk_minhash_bulk_ws(*args, None, 0, None) == 0        # no workspace: one warp per document, same rows
     assert np.array_equal(out, want)

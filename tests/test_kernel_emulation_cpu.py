@@ -189,7 +189,7 @@ def test_deduplication_switches_on_and_off(emu):
 
 @pytest.mark.parametrize("k", [128, 300])
 def test_long_documents_are_cut_into_pieces_on_the_device(emu, k):
-    """signature_kernel.cu piece mode (thresholds shrunk to 100 / 40 tokens so the emulation stays small): the warp that
+    """signature_kernel.cu piece mode (thresholds shrunk to 100 / 32 tokens so the emulation stays small): the warp that
     meets a long document stores the row's initial value and appends pieces; the second launch min-merges them with
     atomicMin.  Mixed with short / empty documents, running-state merge, u64 output, K sliced over blockIdx.y (k = 300)."""
     lib = emu.lib
@@ -209,13 +209,13 @@ def test_long_documents_are_cut_into_pieces_on_the_device(emu, k):
     for dpu, gx in ((3, 1), (1, 2), (32, 2)):
         out = np.zeros((n, k), dtype=np.uint32)
         assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, None, 0, 0,
-                                        out.ctypes.data, 0, dpu, gx, 100, 40, ctypes.byref(npieces)) == 0
+                                        out.ctypes.data, 0, dpu, gx, 100, 5, ctypes.byref(npieces)) == 0
         assert np.array_equal(out, want), (dpu, gx)
-        assert npieces.value == sum(-(-int(x) // 40) for x in lens if x > 100)      # 250, 101, 1000, 481, 3000
+        assert npieces.value == sum(-(-int(x) // 32) for x in lens if x > 100)      # 250, 101, 1000, 481, 3000
     init = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64)
     out64 = np.zeros((n, k), dtype=np.uint64)
     assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, init.ctypes.data, k, 1,
-                                    out64.ctypes.data, 1, 2, 2, 100, 40, None) == 0
+                                    out64.ctypes.data, 1, 2, 2, 100, 5, None) == 0
     assert np.array_equal(out64, np.minimum(want.astype(np.uint64), init))
 
 
