@@ -35,30 +35,33 @@ __device__ __forceinline__ bool tuple_eq(const uint32_t *a, const uint32_t *b, i
     return eq;
 }
 
-// warp <-> new document.  The row is read ONCE with coalesced loads: each value goes to the index's own copy of the
-// signatures (candidates are verified on the r-tuples themselves) and to a shared-memory line, from which lane j takes
-// band j's r-tuple for the fingerprint.  DRAM traffic per document: 4K in, 4K out (the copy), b x 16 bytes of table /
-// chain updates -- the separate device-to-device copy and the b uncoalesced re-reads of the row of the first version
-// (thread <-> (document, band)) are gone.  next[] is laid out [doc][band], so a document's b links are one coalesced store.
+// CTA <-> tile of D = 256 / b new documents.  The tile's rows are contiguous: they are read ONCE with fully coalesced
+// loads, each value going to the index's own copy of the signatures (candidates are verified on the r-tuples
+// themselves) and to shared memory; then thread <-> (document, band) takes its r-tuple from shared memory for the
+// fingerprint and does the table update -- every thread has one atomicCAS chain in flight, which is what hides the DRAM
+// latency of the (much larger than L2) tables.  next[] is laid out [doc][band], so the tile's links are one coalesced
+// store.  The separate device-to-device copy and the b uncoalesced re-reads of each row of the first version are gone.
 __global__ void __launch_bounds__(256) lsh_insert_kernel(const LshDev ix, const uint32_t *__restrict__ new_sig,
-                                                         int64_t doc0, int64_t n_new) {
+                                                         int64_t doc0, int64_t n_new, int docs_per_tile) {
     DSK_DYNAMIC_SMEM_T(uint32_t, s_rows, 16);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint32_t *srow = s_rows + (size_t)w * ix.k;
     const uint64_t mask = (uint64_t)ix.cap_slots - 1;
-    for (int64_t i = (int64_t)blockIdx.x * nw + w; i < n_new; i += (int64_t)gridDim.x * nw) {
-        const int64_t doc = doc0 + i;
-        const uint32_t *row = new_sig + i * ix.k;
-        uint32_t *keep = ix.sig + doc * ix.k;
-        __syncwarp();
-        for (int c = lane; c < ix.k; c += 32) {
-            const uint32_t v = __ldg(row + c);
-            srow[c] = v;
-            keep[c] = v;
+    const int64_t n_tiles = (n_new + docs_per_tile - 1) / docs_per_tile;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * docs_per_tile;
+        const int nd = (int)min((int64_t)docs_per_tile, n_new - i0);
+        const uint32_t *src = new_sig + i0 * ix.k;
+        uint32_t *keep = ix.sig + (doc0 + i0) * ix.k;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nd * ix.k; e += blockDim.x) {
+            const uint32_t v = __ldg(src + e);
+            s_rows[e] = v;
+            keep[e] = v;
         }
-        __syncwarp();
-        for (int band = lane; band < ix.b; band += 32) {
-            const uint64_t fp = band_fp(srow + band * ix.r, ix.r, band);
+        __syncthreads();
+        for (int pair = threadIdx.x; pair < nd * ix.b; pair += blockDim.x) {
+            const int i = pair / ix.b, band = pair - i * ix.b;
+            const int64_t doc = doc0 + i0 + i;
+            const uint64_t fp = band_fp(s_rows + i * ix.k + band * ix.r, ix.r, band);
             uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
             uint64_t slot = lsh_mix64(fp) & mask;
             while (true) {
@@ -177,14 +180,15 @@ __global__ void __launch_bounds__(kScanBlock) scan_add_kernel(int64_t *out, int6
 cudaError_t launch_lsh_insert(const LshDev &ix, const uint32_t *new_sig, int64_t doc0, int64_t n_new, int sm_count,
                               cudaStream_t s) {
     if (n_new <= 0) return cudaSuccess;
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * ix.k * 4 > 64 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * ix.k * 4;
+    int docs_per_tile = 256 / ix.b;                       // one (document, band) pair per thread
+    if (docs_per_tile < 1) docs_per_tile = 1;
+    while (docs_per_tile > 1 && (size_t)docs_per_tile * ix.k * 4 > 48 * 1024) --docs_per_tile;
+    const size_t smem = (size_t)docs_per_tile * ix.k * 4;
     cudaError_t e = cudaFuncSetAttribute(lsh_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t grid = (n_new + warps - 1) / warps;
+    int64_t grid = (n_new + docs_per_tile - 1) / docs_per_tile;
     if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
-    DSK_LAUNCH(lsh_insert_kernel, (unsigned)grid, warps * 32, smem, s, ix, new_sig, doc0, n_new);
+    DSK_LAUNCH(lsh_insert_kernel, (unsigned)grid, 256, smem, s, ix, new_sig, doc0, n_new, docs_per_tile);
     return cudaGetLastError();
 }
 

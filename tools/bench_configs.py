@@ -47,12 +47,18 @@ def c3(n_docs, t=128, k=256, n_query=100_000):
     off = torch.arange(0, (n_docs + 1) * t, t, dtype=torch.int64, device="cuda")
     sig = torch.empty((n_docs, k), dtype=torch.int32, device="cuda")
     ms_sig = ev_time(lambda: dsk.engine.bulk_signatures_device(tok.view(-1), off, n_docs * t, perms, d_out=sig))
+    warm = dsk.GpuLSH(threshold=0.8, num_perm=k, capacity=4096)
+    warm.insert(sig[:4096])                      # first launch of the kernels (module load, attribute set) is not timed
+    warm.query(sig[:64], to_host=False)
+    del warm
     lsh = dsk.GpuLSH(threshold=0.8, num_perm=k, capacity=n_docs)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     lsh.insert(sig)
+    e1.record()
     torch.cuda.synchronize()
-    ms_ins = (time.perf_counter() - t0) * 1e3
+    ms_ins = e0.elapsed_time(e1)
     q = sig[torch.randint(0, n_docs, (n_query,), device="cuda", generator=g)]
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -89,7 +95,7 @@ def c4(n_vec, dim=4096, ss=128):
     h = gen._handle(0)
     out = torch.empty((n_vec, ss, 2), dtype=torch.int64, device="cuda")
     st = torch.empty((n_vec,), dtype=torch.int32, device="cuda")
-    ms = ev_time(lambda: nv.check(nv.load().dsk_wmh_minhash(h, v.data_ptr(), n_vec, out.data_ptr(), st.data_ptr(),
+    ms = ev_time(lambda: nv.check(nv.load().dsk_wmh_minhash(h, v.data_ptr(), n_vec, out.data_ptr(), st.data_ptr(), 0,
                                                              torch.cuda.current_stream().cuda_stream)), iters=2)
     par = o.wmh_params(dim, ss, 1)
     vs = v[:20].cpu().numpy()
