@@ -643,11 +643,9 @@ int dsk_lsh_create(int num_perm, int b, int r, int64_t capacity_docs, int device
     cudaError_t e = cudaSetDevice(device);
     const size_t slots = (size_t)b * v.cap_slots;
     if (e == cudaSuccess) e = cudaMalloc(&v.sig, (size_t)capacity_docs * num_perm * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&v.slot_key, slots * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&v.slot_head, slots * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&v.slots, slots * 2 * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(&v.next, (size_t)b * capacity_docs * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMemset(v.slot_key, 0xFF, slots * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMemset(v.slot_head, 0xFF, slots * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(v.slots, 0xFF, slots * 2 * sizeof(uint64_t));   // empty key, head = -1
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         int rc2 = cuda_fail(e, "dsk_lsh_create");
@@ -664,8 +662,7 @@ void dsk_lsh_destroy(dsk_lsh *ix) {
     cudaGetDevice(&prev);
     cudaSetDevice(ix->device);
     if (ix->dev.sig) cudaFree(ix->dev.sig);
-    if (ix->dev.slot_key) cudaFree(ix->dev.slot_key);
-    if (ix->dev.slot_head) cudaFree(ix->dev.slot_head);
+    if (ix->dev.slots) cudaFree(ix->dev.slots);
     if (ix->dev.next) cudaFree(ix->dev.next);
     cudaSetDevice(prev);
     delete ix;

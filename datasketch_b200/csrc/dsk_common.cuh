@@ -102,8 +102,9 @@ cudaError_t launch_wmh(const float *rs_t, const float *lncs_t, const float *beta
 // ---- device-resident LSH index (lsh_kernels.cu) -------------------------------------------------
 struct LshDev {
     uint32_t *sig;        // [cap_docs][k] copies of the inserted signatures (tuple verification)
-    uint64_t *slot_key;   // [b][cap_slots]
-    int32_t *slot_head;   // [b][cap_slots]  most recently inserted doc of the bucket, -1 = none
+    // [b][cap_slots] 16-byte slots {uint64 fingerprint, int32 head, int32 unused}: the claim (atomicCAS on the key) and the
+    // chain update (atomicExch on the head = most recently inserted doc of the bucket, -1 = none) touch ONE 32-byte sector
+    uint64_t *slots;
     int32_t *next;        // [cap_docs][b]   next doc in the same bucket of that band, -1 = end
     int64_t cap_docs, cap_slots;  // cap_slots is a power of two >= 2 * cap_docs
     int k, b, r;

@@ -62,15 +62,15 @@ __global__ void __launch_bounds__(256) lsh_insert_kernel(const LshDev ix, const 
             const int i = pair / ix.b, band = pair - i * ix.b;
             const int64_t doc = doc0 + i0 + i;
             const uint64_t fp = band_fp(s_rows + i * ix.k + band * ix.r, ix.r, band);
-            uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
+            uint64_t *tab = ix.slots + (int64_t)band * ix.cap_slots * 2;
             uint64_t slot = lsh_mix64(fp) & mask;
             while (true) {
-                const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(keys + slot),
+                const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(tab + 2 * slot),
                                                           (unsigned long long)kEmptyKey, (unsigned long long)fp);
                 if (prev == kEmptyKey || prev == fp) break;
                 slot = (slot + 1) & mask;
             }
-            const int32_t old = atomicExch(ix.slot_head + (int64_t)band * ix.cap_slots + slot, (int32_t)doc);
+            const int32_t old = atomicExch(reinterpret_cast<int32_t *>(tab + 2 * slot + 1), (int32_t)doc);
             ix.next[doc * ix.b + band] = old;
         }
     }
@@ -99,12 +99,12 @@ __global__ void __launch_bounds__(256) lsh_query_kernel(const LshDev ix, const u
                 if (band < ix.b) {
                     const uint32_t *qt = qrow + (int64_t)band * ix.r;
                     const uint64_t fp = band_fp(qt, ix.r, band);
-                    const uint64_t *keys = ix.slot_key + (int64_t)band * ix.cap_slots;
+                    const uint64_t *tab = ix.slots + (int64_t)band * ix.cap_slots * 2;
                     uint64_t slot = lsh_mix64(fp) & mask;
                     int32_t d = -1;
                     while (true) {
-                        const uint64_t kk = keys[slot];
-                        if (kk == fp) { d = ix.slot_head[(int64_t)band * ix.cap_slots + slot]; break; }
+                        const uint64_t kk = tab[2 * slot];
+                        if (kk == fp) { d = *reinterpret_cast<const int32_t *>(tab + 2 * slot + 1); break; }
                         if (kk == kEmptyKey) break;
                         slot = (slot + 1) & mask;
                     }

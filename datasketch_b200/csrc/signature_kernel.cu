@@ -280,21 +280,29 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                 const int ngrp = (n_eff + 3) >> 2;   // 4-token groups holding at least one real token
 
                 // ---- phase 1: m = smallest key, m2 = second smallest, key = (block min L' & ~31) | block -------
-                uint32_t m[P], m2[P];
+                // The tracking ops of a block are folded in while the NEXT block's IMADs issue (pend = the previous block's
+                // key): in program order they sit between IMADs instead of forming a 16-instruction run without a
+                // multiply at every block end -- a warp issues in order, so such a run idles the multiplier unless
+                // another warp happens to be in its IMAD phase.  A pending key of 2^32-1 is a no-op.
+                uint32_t m[P], m2[P], pend[P];
 #pragma unroll
-                for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
+                for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; pend[j] = 0xFFFFFFFFu; }
+                auto fold = [&](int j) {
+                    const uint32_t key = pend[j], om = m[j];
+                    m2[j] = min(m2[j], max(key, om));
+                    m[j] = min(om, key);
+                };
                 auto compute = [&](const uint32_t (&t)[16], uint32_t lb) {
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
                         const uint32_t c = c7[j];
                         uint32_t bm = umin3(alo[j] * t[0] + c, alo[j] * t[1] + c, alo[j] * t[2] + c);
+                        if constexpr (P <= 4) fold(j);           // (P = 8 has no registers to spare for pend[])
 #pragma unroll
                         for (int i = 3; i < 15; i += 2) bm = umin3(bm, alo[j] * t[i] + c, alo[j] * t[i + 1] + c);
                         bm = min(bm, alo[j] * t[15] + c);
-                        const uint32_t key = (bm & ~kKeyMask) | lb;
-                        const uint32_t om = m[j];
-                        m2[j] = min(m2[j], max(key, om));
-                        m[j] = min(om, key);
+                        pend[j] = (bm & ~kKeyMask) | lb;
+                        if constexpr (P > 4) fold(j);
                     }
                 };
                 {
@@ -327,6 +335,11 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                             lb += 2;
                         }
                     }
+                }
+
+                if constexpr (P <= 4) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) fold(j);   // the last block's key
                 }
 
                 // ---- phase 2: exact evaluation inside each permutation's winning block ------------------------

@@ -126,8 +126,8 @@ extern "C" int emu_bbit_unpack(const uint64_t *blocks, int64_t n, int k, int slo
 struct EmuLsh {
     dsk::LshDev dev;
     std::vector<uint32_t> sig;
-    std::vector<uint64_t> slot_key;
-    std::vector<int32_t> slot_head, next;
+    std::vector<uint64_t> slots;
+    std::vector<int32_t> next;
     int64_t n_docs = 0;
 };
 extern "C" void *emu_lsh_create(int k, int b, int r, int64_t cap_docs) {
@@ -137,10 +137,9 @@ extern "C" void *emu_lsh_create(int k, int b, int r, int64_t cap_docs) {
     v.cap_slots = 1024;
     while (v.cap_slots < 2 * cap_docs) v.cap_slots <<= 1;
     ix->sig.assign((size_t)cap_docs * k, 0u);
-    ix->slot_key.assign((size_t)b * v.cap_slots, ~0ull);          // cudaMemset 0xFF
-    ix->slot_head.assign((size_t)b * v.cap_slots, -1);
+    ix->slots.assign((size_t)b * v.cap_slots * 2, ~0ull);        // cudaMemset 0xFF: empty key, head = -1
     ix->next.assign((size_t)b * cap_docs, 0);
-    v.sig = ix->sig.data(); v.slot_key = ix->slot_key.data(); v.slot_head = ix->slot_head.data(); v.next = ix->next.data();
+    v.sig = ix->sig.data(); v.slots = ix->slots.data(); v.next = ix->next.data();
     return ix;
 }
 extern "C" void emu_lsh_destroy(void *h) { delete static_cast<EmuLsh *>(h); }
