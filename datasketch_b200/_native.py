@@ -59,6 +59,9 @@ SIGNATURES = {
     "dsk_exclusive_scan": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dsk_jaccard_pairs": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dsk_jaccard_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dsk_jaccard_topk_workspace_size": (ctypes.c_size_t, [c_int64, c_int64, c_int]),
+    "dsk_jaccard_topk_ws": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                    ctypes.c_size_t, c_void_p]),
     "dsk_sha1_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "dsk_hash_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_int, ctypes.c_uint32, c_void_p, c_void_p]),
     "dsk_bbit_pack": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
@@ -93,7 +96,10 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB
-        if _build._stale() and (_build.have_nvcc() or not os.path.exists(path)):
+        variant = os.environ.get("DSK_B200_LIB")   # kernel A/B experiments (tools/build_variants.sh): another build of the SAME sources
+        if variant:
+            path = variant
+        elif _build._stale() and (_build.have_nvcc() or not os.path.exists(path)):
             try:
                 _build.build()
             except Exception as exc:  # noqa: BLE001

@@ -145,7 +145,7 @@ def jaccard_pairs(sig, i, j, stream=None):
     return cnt.astype(np.float64) / float(k)
 
 
-def jaccard_topk(queries, db, topk: int = 10, self_base: int = -1, to_host: bool = True, stream=None):
+def jaccard_topk(queries, db, topk: int = 10, self_base: int = -1, to_host: bool = True, stream=None, prefilter: bool = True):
     """For every query row: the ``topk`` database rows with the highest Jaccard estimate
     (count of equal positions / K), best first, ties -> lower index.  ``self_base >= 0`` means
     query i *is* database row ``self_base + i`` and is left out of its own list.
@@ -163,8 +163,14 @@ def jaccard_topk(queries, db, topk: int = 10, self_base: int = -1, to_host: bool
     cnt = torch.empty((nq, topk), dtype=torch.int32, device=d_q.device)
     idx = torch.empty((nq, topk), dtype=torch.int64, device=d_q.device)
     with torch.cuda.device(d_q.device):
-        nv.check(nv.load().dsk_jaccard_topk(d_q.data_ptr(), nq, d_db.data_ptr(), d_db.shape[0], k, topk, self_base,
-                                            cnt.data_ptr(), idx.data_ptr(), _stream(d_q, stream)))
+        # the fingerprint prefilter needs a workspace for the bit planes of both matrices (library-sized, owned here)
+        ws_bytes = int(nv.load().dsk_jaccard_topk_workspace_size(nq, d_db.shape[0], k)) if prefilter else 0
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=d_q.device) if ws_bytes else None
+        nv.check(nv.load().dsk_jaccard_topk_ws(d_q.data_ptr(), nq, d_db.data_ptr(), d_db.shape[0], k, topk, self_base,
+                                               cnt.data_ptr(), idx.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                               ws_bytes, _stream(d_q, stream)))
+        if ws is not None and stream is not None:
+            ws.record_stream(torch.cuda.ExternalStream(stream))
     if not to_host:
         return cnt, idx
     c = cnt.cpu().numpy()

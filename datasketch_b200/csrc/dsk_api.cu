@@ -749,8 +749,18 @@ int dsk_jaccard_pairs(const uint32_t *d_sig, int64_t n_rows, int num_perm, const
     return DSK_OK;
 }
 
+size_t dsk_jaccard_topk_workspace_size(int64_t nq, int64_t n, int num_perm) {
+    return (nq < 0 || n < 0) ? 0 : jaccard_topk_workspace_bytes(nq, n, num_perm);
+}
+
 int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
                      int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *stream) {
+    return dsk_jaccard_topk_ws(d_q, nq, d_db, n, num_perm, topk, self_base, d_cnt, d_idx, nullptr, 0, stream);
+}
+
+int dsk_jaccard_topk_ws(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int64_t n, int num_perm, int topk,
+                        int64_t self_base, int32_t *d_cnt, int64_t *d_idx, void *d_workspace, size_t workspace_bytes,
+                        void *stream) {
     if (nq < 0 || n < 0 || num_perm <= 0 || num_perm > 4096 || topk <= 0 || topk > 32 ||
         (nq > 0 && (!d_q || !d_cnt || !d_idx)) || (n > 0 && !d_db)) {
         set_error("dsk_jaccard_topk: bad arguments (need 0 < topk <= 32, 0 < num_perm <= 4096)");
@@ -760,11 +770,20 @@ int dsk_jaccard_topk(const uint32_t *d_q, int64_t nq, const uint32_t *d_db, int6
         set_error("dsk_jaccard_topk: d_db must be 16-byte aligned");
         return DSK_ERR_ALIGN;
     }
+    const size_t need = jaccard_topk_workspace_bytes(nq, n, num_perm);
+    if (d_workspace && (((uintptr_t)d_workspace & 15) != 0 || workspace_bytes < need)) {
+        set_error("dsk_jaccard_topk_ws: workspace must be 16-byte aligned and hold dsk_jaccard_topk_workspace_size() = %zu bytes", need);
+        return DSK_ERR_INVALID;
+    }
     DevInfo *dev;
     int rc = current_dev(&dev);
     if (rc) return rc;
-    DSK_CUDA(launch_jaccard_topk(d_q, nq, d_db, n, num_perm, topk, self_base, d_cnt, d_idx, dev->sm_count,
-                                 (cudaStream_t)stream));
+    if (d_workspace && need > 0)   // fingerprint prefilter, then exact counts of the surviving pairs
+        DSK_CUDA(launch_jaccard_topk_pf(d_q, nq, d_db, n, num_perm, topk, self_base, d_cnt, d_idx, d_workspace, dev->sm_count,
+                                        (cudaStream_t)stream));
+    else
+        DSK_CUDA(launch_jaccard_topk(d_q, nq, d_db, n, num_perm, topk, self_base, d_cnt, d_idx, dev->sm_count,
+                                     (cudaStream_t)stream));
     return DSK_OK;
 }
 

@@ -121,6 +121,11 @@ cudaError_t launch_jaccard_pairs(const uint32_t *sig, int64_t n_rows, int k, con
 cudaError_t launch_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *db, int64_t n, int k, int topk,
                                 int64_t self_base, int32_t *out_cnt, int64_t *out_idx, int sm_count, cudaStream_t s);
 
+size_t jaccard_topk_workspace_bytes(int64_t nq, int64_t n, int k);
+cudaError_t launch_jaccard_topk_pf(const uint32_t *q, int64_t nq, const uint32_t *db, int64_t n, int k, int topk,
+                                   int64_t self_base, int32_t *out_cnt, int64_t *out_idx, void *workspace, int sm_count,
+                                   cudaStream_t s);
+
 cudaError_t launch_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, void *out, int out_is_u64,
                                int sm_count, cudaStream_t s);
 cudaError_t launch_hash_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, int kind, uint32_t seed,

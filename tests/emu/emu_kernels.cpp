@@ -178,6 +178,15 @@ extern "C" int emu_jaccard_topk(const uint32_t *q, int64_t nq, const uint32_t *d
                                 int64_t self_base, int32_t *out_cnt, int64_t *out_idx, int sm_count) {
     return dsk::launch_jaccard_topk(q, nq, db, n, k, topk, self_base, out_cnt, out_idx, sm_count, nullptr);
 }
+// the fingerprint-prefilter variant (its own workspace for the bit planes), any n
+extern "C" int emu_jaccard_topk_pf(const uint32_t *q, int64_t nq, const uint32_t *db, int64_t n, int k, int topk,
+                                   int64_t self_base, int32_t *out_cnt, int64_t *out_idx, int sm_count) {
+    const int words = (k + 31) / 32;
+    const size_t qt = (size_t)((nq + dsk::kTQ - 1) / dsk::kTQ), dt = (size_t)((n + dsk::kTD - 1) / dsk::kTD);
+    std::vector<uint32_t> ws((qt * dsk::kTQ + dt * dsk::kTD) * (size_t)dsk::kPfB * words + 8, 0xCDCDCDCDu);
+    uint32_t *wsp = ws.data() + ((16 - (reinterpret_cast<uintptr_t>(ws.data()) & 15)) % 16) / 4;
+    return dsk::launch_jaccard_topk_pf(q, nq, db, n, k, topk, self_base, out_cnt, out_idx, wsp, sm_count, nullptr);
+}
 extern "C" int emu_sha1_tokens(const uint8_t *bytes, const int64_t *off, int64_t n_tok, void *out, int out_is_u64) {
     return dsk::launch_sha1_tokens(bytes, off, n_tok, out, out_is_u64, 1, nullptr);
 }

@@ -431,6 +431,37 @@ def test_jaccard_pairs_and_topk_kernels(emu):
         assert np.array_equal(oc_idx[i], order) and np.array_equal(oc_cnt[i], c[order])
 
 
+@pytest.mark.parametrize("k,n,nq,topk,vals", [(64, 300, 70, 5, 3), (128, 520, 64, 10, 1 << 32), (100, 257, 130, 7, 50), (32, 140, 10, 32, 2)])
+def test_topk_with_fingerprint_prefilter_equals_exact(emu, k, n, nq, topk, vals):
+    """jaccard_topk_pf_kernel: bit-sliced 16-bit fingerprints give an upper bound of the match count; only pairs whose bound
+    could still enter the list are counted exactly -- the lists must equal a brute-force ranking (and the exact kernel's):
+    heavy ties (3 distinct values), no similarity at all (random 32-bit), K not a multiple of 32, topk = 32."""
+    lib = emu.lib
+    rs = np.random.RandomState(k + n)
+    db = rs.randint(0, vals, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    db[rs.randint(0, n, 25)] = db[rs.randint(0, n, 25)]                # exact duplicates
+    near = rs.randint(0, n, 40)
+    db[near, : k // 2] = db[rs.randint(0, n, 40), : k // 2]             # half-equal rows
+    base = 17
+    q = np.ascontiguousarray(db[base:base + nq])
+    for self_base in (base, -1):
+        got_c = np.zeros((nq, topk), dtype=np.int32)
+        got_i = np.zeros((nq, topk), dtype=np.int64)
+        assert lib.emu_jaccard_topk_pf(_ptr(q), ctypes.c_int64(nq), _ptr(db), ctypes.c_int64(n), k, topk,
+                                       ctypes.c_int64(self_base), _ptr(got_c), _ptr(got_i), 1) == 0
+        ex_c, ex_i = np.zeros_like(got_c), np.zeros_like(got_i)
+        assert lib.emu_jaccard_topk(_ptr(q), ctypes.c_int64(nq), _ptr(db), ctypes.c_int64(n), k, topk,
+                                    ctypes.c_int64(self_base), _ptr(ex_c), _ptr(ex_i), 1) == 0
+        assert np.array_equal(got_c, ex_c) and np.array_equal(got_i, ex_i)
+        for i in range(0, nq, 7):
+            c = (db == q[i][None, :]).sum(axis=1).astype(np.int64)
+            order = np.lexsort((np.arange(n), -c))
+            if self_base >= 0:
+                order = order[order != self_base + i]
+            order = order[:topk]
+            assert np.array_equal(got_i[i], order) and np.array_equal(got_c[i], c[order])
+
+
 def test_sha1_kernel_vs_hashlib(emu):
     import hashlib
     import struct
