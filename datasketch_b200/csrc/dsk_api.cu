@@ -1035,7 +1035,17 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
             {
                 const int64_t piece = piece_len(h_offsets[d1] - t0);
                 int64_t ext = 0;
-                for (int64_t i = d0; i < d1; ++i) ext += n_pieces(h_offsets[i + 1] - h_offsets[i], piece);
+                bool decreasing = false;   // every interior offset is checked here, in the pass that reads them anyway
+                for (int64_t i = d0; i < d1; ++i) {
+                    const int64_t len = h_offsets[i + 1] - h_offsets[i];
+                    decreasing |= len < 0;
+                    ext += n_pieces(len, piece);
+                }
+                if (decreasing) {
+                    cudaSetDevice(prev);
+                    set_error("dsk_minhash_bulk_host: offsets must be non-decreasing");
+                    return DSK_ERR_INVALID;
+                }
                 if (ext != d1 - d0) {
                     biggest_ext = biggest_ext > ext ? biggest_ext : ext;
                     biggest_split_docs = biggest_split_docs > d1 - d0 ? biggest_split_docs : d1 - d0;

@@ -92,28 +92,6 @@ void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int6
     }
 }
 
-// compile-time switches for kernel A/B experiments (tools/build_variants.sh); the defaults are the product
-#ifdef DSK_SIG_NO_PEND
-template <int P> constexpr bool kPend = false;
-#else
-template <int P> constexpr bool kPend = P <= 4;
-#endif
-#ifdef DSK_SIG_NO_DEFER
-constexpr bool kDeferLong = false;
-#else
-constexpr bool kDeferLong = true;
-#endif
-#ifdef DSK_SIG_NO_SWP
-constexpr bool kSwPipe = false;
-#else
-constexpr bool kSwPipe = true;
-#endif
-#ifdef DSK_SIG_G2
-constexpr int kPhase2Group = 2;
-#else
-constexpr int kPhase2Group = 4;
-#endif
-
 template <int P, int OCC, bool PIECES>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
     __shared__ __align__(128) uint32_t s_ring[kSigWarps][kRingTok];
@@ -243,7 +221,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
             // a long document is cut into pieces for the second launch; here only its initial row gets stored below
             bool defer = false;
             if constexpr (!PIECES) {
-                defer = kDeferLong && prm.long_doc_tokens > 0 && end - start > prm.long_doc_tokens;
+                defer = prm.long_doc_tokens > 0 && end - start > prm.long_doc_tokens;
                 if (defer && blockIdx.y == 0) append_pieces(prm.piece_hdr, prm.pieces, prm.piece_shift, d, start, end, lane);
             }
 
@@ -302,36 +280,30 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                 const int ngrp = (n_eff + 3) >> 2;   // 4-token groups holding at least one real token
 
                 // ---- phase 1: m = smallest key, m2 = second smallest, key = (block min L' & ~31) | block -------
-                // The tracking ops of a block are folded in while the NEXT block's IMADs issue (pend = the previous block's
-                // key): in program order they sit between IMADs instead of forming a 16-instruction run without a
-                // multiply at every block end -- a warp issues in order, so such a run idles the multiplier unless
-                // another warp happens to be in its IMAD phase.  A pending key of 2^32-1 is a no-op.
-                uint32_t m[P], m2[P], pend[P];
+                uint32_t m[P], m2[P];
 #pragma unroll
-                for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; pend[j] = 0xFFFFFFFFu; }
-                auto fold = [&](int j) {
-                    const uint32_t key = pend[j], om = m[j];
-                    m2[j] = min(m2[j], max(key, om));
-                    m[j] = min(om, key);
-                };
+                for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
+                // (Folding a block's four tracking ops in during the NEXT block's IMADs -- so that no run of 16 non-multiply
+                // instructions ends each block -- was measured: no gain, profiles/r2i_kernel_variants_ab.txt.)
                 auto compute = [&](const uint32_t (&t)[16], uint32_t lb) {
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
                         const uint32_t c = c7[j];
                         uint32_t bm = umin3(alo[j] * t[0] + c, alo[j] * t[1] + c, alo[j] * t[2] + c);
-                        if constexpr (kPend<P>) fold(j);         // (P = 8 has no registers to spare for pend[])
 #pragma unroll
                         for (int i = 3; i < 15; i += 2) bm = umin3(bm, alo[j] * t[i] + c, alo[j] * t[i + 1] + c);
                         bm = min(bm, alo[j] * t[15] + c);
-                        pend[j] = (bm & ~kKeyMask) | lb;
-                        if constexpr (!kPend<P>) fold(j);
+                        const uint32_t key = (bm & ~kKeyMask) | lb;
+                        const uint32_t om = m[j];
+                        m2[j] = min(m2[j], max(key, om));
+                        m[j] = min(om, key);
                     }
                 };
                 {
                     const uint32_t *q = src;
                     const uint32_t *const qe = src + nblk * 16;
                     uint32_t lb = 0;
-                    if constexpr (P > 4 || !kSwPipe) {
+                    if constexpr (P > 4) {
 #pragma unroll 1
                         for (; q < qe; q += 16, ++lb) {
                             uint32_t t[16];
@@ -359,15 +331,11 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                     }
                 }
 
-                if constexpr (kPend<P>) {
-#pragma unroll
-                    for (int j = 0; j < P; ++j) fold(j);   // the last block's key
-                }
-
                 // ---- phase 2: exact evaluation inside each permutation's winning block ------------------------
                 uint32_t res[P], win[P];   // win: upper end of the L' window the flagged path must evaluate
                 unsigned need_slow = 0;
-                constexpr int G = P < kPhase2Group ? P : kPhase2Group;   // permutations handled together (bounds live registers)
+                // permutations handled together: 2 measured best for P <= 4, 4 for P = 8 (profiles/r2i_kernel_variants_ab.txt)
+                constexpr int G = P > 4 ? 4 : (P < 2 ? P : 2);
 #pragma unroll
                 for (int j0 = 0; j0 < P; j0 += G) {
                     uint4 v[G][4];
@@ -562,27 +530,12 @@ static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-// CTAs per SM the kernel is compiled for (register cap = 65536 / (128 * OCC)); DSK_SIG_OCC = 4 | 5 for experiments
-static int sig_occ() {
-    static int occ = [] {
-        const char *e = getenv("DSK_SIG_OCC");
-        const int v = e ? atoi(e) : 4;
-        return (v == 4 || v == 5 || v == 6) ? v : 4;
-    }();
-    return occ;
-}
-
+// 4 CTAs (16 warps) per SM: 5 and 6 were measured slower (register cap, profiles/r2i_kernel_variants_ab.txt)
 cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s) {
     if (prm.k <= 32) return launch_sig<1, 4>(prm, sm_count, s);
     if (prm.k <= 64) return launch_sig<2, 4>(prm, sm_count, s);
     if (prm.k <= 128) {
-        switch (sig_occ()) {
-            case 5: return launch_sig<4, 5>(prm, sm_count, s);
-#ifdef DSK_SIG_NO_SWP
-            case 6: return launch_sig<4, 6>(prm, sm_count, s);
-#endif
-            default: return launch_sig<4, 4>(prm, sm_count, s);
-        }
+        return launch_sig<4, 4>(prm, sm_count, s);
     }
     return launch_sig<8, 4>(prm, sm_count, s);
 }

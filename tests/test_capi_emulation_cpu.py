@@ -316,3 +316,15 @@ def test_minhash_bulk_ws_cuts_long_documents(emu_lib):
     assert lib.dsk_minhash_bulk_ws(*args, ws.ctypes.data, need - 1, None) != 0 and b"workspace" in lib.dsk_last_error()
     assert lib.dsk_minhash_bulk_ws(*args, ws.ctypes.data + 4, need, None) != 0
     lib.dsk_perm_destroy(h)
+
+
+def test_interior_offsets_are_validated_by_the_library(dsk_on_emu):
+    """A decreasing interior offset is refused by dsk_minhash_bulk_host (DSK_ERR_INVALID -> ValueError) before any
+    token is indexed with it -- including one hidden inside a slice whose end points look fine."""
+    dsk = dsk_on_emu
+    P = dsk.minhash._make_permutations(16, 1)
+    tok = np.arange(10, dtype=np.uint32)
+    for off in ([0, 6, 4, 10], [0, 2, 9, 3, 10], [0, 10, 0, 10]):
+        with pytest.raises(ValueError):
+            dsk.engine.bulk_signatures(tok, np.array(off, dtype=np.int64), P)
+    assert dsk.engine.bulk_signatures(tok, np.array([0, 4, 4, 10], dtype=np.int64), P).shape == (3, 16)
