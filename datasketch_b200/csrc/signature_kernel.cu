@@ -534,9 +534,10 @@ static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream
 cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s) {
     if (prm.k <= 32) return launch_sig<1, 4>(prm, sm_count, s);
     if (prm.k <= 64) return launch_sig<2, 4>(prm, sm_count, s);
-    if (prm.k <= 128) {
-        return launch_sig<4, 4>(prm, sm_count, s);
-    }
+    if (prm.k <= 128) return launch_sig<4, 4>(prm, sm_count, s);
+    // K > 128: 8 permutations per lane, or (DSK_SIG_WIDE=4, an A/B switch) K-slices of 128 on blockIdx.y with 4 per lane
+    static const bool wide4 = [] { const char *e = getenv("DSK_SIG_WIDE"); return e && atoi(e) == 4; }();
+    if (wide4) return launch_sig<4, 4>(prm, sm_count, s);
     return launch_sig<8, 4>(prm, sm_count, s);
 }
 
