@@ -1,0 +1,98 @@
+"""The two-phase signature kernel (csrc/signature_kernel.cu) on the GPU against the C oracle: a randomised sweep over
+the shapes that take its different paths -- in-place vs copied staging, ring wrap, sub-pieces, padding groups, repeated
+tokens (flagged permutations, de-duplicating staging), tiny values next to the L'-7 wrap, long documents cut into pieces
+on the device, K slices, running state, u64 output -- through the device-buffer entry (`dsk_minhash_bulk_ws`).
+Reference: datasketch/minhash.py:294-297 (update_batch), :464-522 (bulk); oracle = oracle/oracle_c.c (pinned to the
+reference's fixtures by tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_clib as oc
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(rs, style):
+    if style == 0:      # aligned, in place
+        t = int(rs.choice([16, 64, 256, 512, 1024]))
+        lens = np.full(int(rs.randint(50, 400)), t)
+    elif style == 1:    # ragged short
+        lens = rs.randint(0, 120, size=int(rs.randint(100, 2000)))
+    elif style == 2:    # ragged medium, some empty
+        lens = rs.randint(0, 700, size=int(rs.randint(50, 600)))
+        lens[rs.randint(0, len(lens), 5)] = 0
+    elif style == 3:    # a few long documents between short ones
+        lens = rs.randint(0, 300, size=int(rs.randint(20, 200)))
+        for i in rs.randint(0, len(lens), 4):
+            lens[i] = int(rs.choice([4096, 4097, 5000, 20_000, 70_000]))
+    else:               # one block / one group documents
+        lens = rs.randint(1, 20, size=int(rs.randint(200, 3000)))
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    T = int(off[-1])
+    tok = rs.randint(0, 1 << 32, size=T + 1, dtype=np.uint64).astype(np.uint32)[:T]
+    u = rs.uniform()
+    if u < 0.4 and T > 2:         # repeated tokens inside documents
+        share = rs.uniform(0.01, 0.7)
+        doc = np.repeat(np.arange(len(lens)), lens)
+        pos = np.arange(T) - off[doc]
+        rep = (rs.uniform(size=T) < share) & (pos > 0)
+        src = off[doc] + (rs.uniform(size=T) * pos).astype(np.int64)
+        tok = np.where(rep, tok[src], tok)
+    elif u < 0.55 and T > 0:      # tiny / huge values: products next to the wrap, many exact ties
+        tok[: T // 2] = rs.randint(0, 30, size=T // 2)
+        tok[T // 2:] = (np.uint64(1 << 32) - rs.randint(1, 30, size=T - T // 2).astype(np.uint64)).astype(np.uint32)
+    return np.ascontiguousarray(tok), off
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_shapes_against_the_oracle(seed):
+    import torch
+    import datasketch_b200 as dsk
+    rs = np.random.RandomState(1000 + seed)
+    for it in range(10):
+        style = int(rs.randint(0, 5))
+        tok, off = _case(rs, style)
+        k = int(rs.choice([16, 64, 100, 128, 128, 128, 200, 256, 300]))
+        P = o.init_permutations(k, int(rs.randint(1, 40)))
+        want = oc.minhash_bulk_u32tok(tok, off, P).astype(np.uint64)
+        n = len(off) - 1
+        d_tok = torch.from_numpy(np.concatenate([tok, np.zeros(4, np.uint32)]).view(np.int32)).cuda()[:len(tok)]
+        d_off = torch.from_numpy(off).cuda()
+        mode = int(rs.randint(0, 3))
+        if mode == 0:
+            got = dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P).cpu().numpy().view(np.uint32).astype(np.uint64)
+        else:
+            init = rs.randint(0, 1 << 32, size=(n, k) if mode == 1 else (1, k), dtype=np.uint64)
+            d_init = torch.from_numpy(init.view(np.int64)).cuda()
+            d_out = torch.empty((n, k), dtype=torch.int64, device="cuda")
+            dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P, d_out=d_out, d_init=d_init,
+                                              init_stride=k if mode == 1 else 0)
+            got = d_out.cpu().numpy().view(np.uint64)
+            want = np.minimum(want, init if mode == 1 else init[0][None, :])
+        assert np.array_equal(got, want), dict(seed=seed, it=it, style=style, k=k, mode=mode, docs=n, tokens=len(tok))
+
+
+def test_repeated_calls_reuse_counters_and_workspace():
+    """More launches of one permutation handle than it has counter sets (64), on two streams, with long documents in every
+    batch: the leases (event-guarded) and the per-call workspaces keep every result equal to the oracle's."""
+    import torch
+    import datasketch_b200 as dsk
+    rs = np.random.RandomState(5)
+    lens = np.array([300] * 30 + [9000, 40, 12_000], dtype=np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+    P = o.init_permutations(128, 3)
+    want = oc.minhash_bulk_u32tok(tok, off, P)
+    d_tok = torch.from_numpy(tok.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for i in range(150):
+        with torch.cuda.stream(streams[i & 1]):
+            outs.append(dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P))
+    torch.cuda.synchronize()
+    for i in (0, 1, 63, 64, 65, 128, 149):
+        assert np.array_equal(outs[i].cpu().numpy().view(np.uint32), want), i
