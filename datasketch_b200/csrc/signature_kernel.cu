@@ -21,10 +21,13 @@
 //            key = (block min & ~31) | block index:  m = smallest key, m2 = second smallest.
 //   phase 2  per permutation: recompute L' on the winning block (block index = m & 31), find the one 4-token group
 //            inside the +7 window and evaluate those 4 tokens exactly (groups that hold padding only are ignored).
+//   long     with a caller-provided piece table (dsk_minhash_bulk_ws) a document longer than 4096 tokens is not processed
+//            where it is met: its row gets the initial value and ceil(len / 1024) piece descriptors are appended; a
+//            second launch (template flag PIECES) spreads the pieces over all warps and min-merges with atomicMin.
 //   flagged  a permutation with another block inside the window (m2 - m <= 69), a second group inside the window,
 //            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp, two permutations
 //            at a time: every lane filters 1/32 of the sub-piece's tokens with L' and evaluates r exactly for the
-//            ones inside the window, then one redux.sync.min.  Exact for any input; ~40 issue slots per flagged
+//            ones inside the window, then one redux.sync.min.  Exact for any input; ~55 issue slots per flagged
 //            (document, permutation).  A sub-piece with >= 8 flagged permutations (repeated tokens) switches the
 //            warp to de-duplicating staging, which removes the ties at their source.
 #include "dsk_common.cuh"
@@ -37,7 +40,7 @@ constexpr int kChunkShift = 8;      // 256 tokens = 1 KB per TMA bulk copy / rin
 constexpr int kChunkTok = 1 << kChunkShift;
 constexpr int kRingSlots = kRingTok / kChunkTok;
 constexpr int kSubTok = 512;        // tokens per sub-piece
-constexpr int kTabSlots = 1024;     // dedupe hash set (load factor <= 0.5)
+constexpr int kTabSlots = 1024;     // de-duplication table: one slot per hashed token value, later tokens overwrite earlier ones
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kKeyMask = 31u;  // low bits of a tracking key hold the block index (32 blocks of 16 tokens)
 constexpr uint32_t kNearWindow = 7u + 2u * kKeyMask;  // m2 - m <= this: another block may be inside the +7 window
