@@ -43,6 +43,18 @@ for n, k, b, r in [(2_000_000, 128, 9, 13), (1_000_000, 256, 17, 15)]:
     ms = timeit(lambda: dsk.codec.band_fingerprints(sig, b, r))
     by = n * (4 * b * r + 8 * b)
     out.append({"kernel": "band_fingerprints", "n": n, "k": k, "b": b, "r": r, "ms": ms, "GBps": by / ms / 1e6, "frac": by / ms / 1e6 / peak})
-    del sig, rec
+    ms = timeit(lambda: dsk.codec.band_sums(sig, b, r))
+    by = n * (4 * b * r + 8 * b)
+    out.append({"kernel": "band_sums (LSHBloom keys)", "n": n, "k": k, "b": b, "r": r, "ms": ms, "GBps": by / ms / 1e6, "frac": by / ms / 1e6 / peak})
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bl = dsk.MinHashLSHBloom(num_perm=k, n=n, fp=0.001, params=(b, r))
+    ms = timeit(lambda: bl.insert_batch(sig), iters=3, warm=1)
+    out.append({"kernel": "bloom insert (keys + %d probes x %d bands)" % (bl.n_hashes, b), "n": n, "k": k, "ms": ms, "docs_per_s": n / ms * 1e3,
+                "table_MB": bl.b * bl.words_per_table * 4 / 1e6})
+    ms = timeit(lambda: bl.query_batch(sig, to_host=False), iters=3, warm=1)
+    out.append({"kernel": "bloom query", "n": n, "k": k, "ms": ms, "docs_per_s": n / ms * 1e3})
+    del sig, rec, bl
 for o in out:
     print(json.dumps(o))
