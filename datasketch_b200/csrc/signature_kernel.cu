@@ -76,10 +76,12 @@ __device__ __forceinline__ void load_block16(const uint32_t *src, uint32_t (&t)[
 }
 
 // A long document's pieces (2^piece_shift tokens each) go to the table the second launch works through.
-#ifndef DSK_EMU
-__device__ __forceinline__
-#else
+#ifdef DSK_EMU
 static inline
+#elif DSK_SIG_APPEND_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
 #endif
 void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int64_t row, int64_t start, int64_t end, int lane) {
     const int64_t step = (int64_t)1 << piece_shift;
@@ -94,6 +96,24 @@ void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int6
         pieces[base + q] = pd;
     }
 }
+
+// Code-generation switches.  The kernel's speed moves by several per cent with changes that do not touch the block loop
+// (ptxas schedules / allocates the whole kernel at once), so the combination in use was picked by timing builds of the same
+// sources with different -D values on one box (tools/build_variants.sh + tools/ab_libs.py, profiles/r2r_kernel_codegen_grid.txt:
+// 16 combinations span 2.94 .. 3.14 ms on the C2 shape; the defaults below are the fastest one).
+#ifndef DSK_SIG_PEND
+#define DSK_SIG_PEND 1          // fold a block's tracking ops in during the next block's IMADs (P <= 4 only)
+#endif
+#ifndef DSK_SIG_G
+#define DSK_SIG_G 4             // permutations handled together in phase 2 (P <= 4)
+#endif
+#ifndef DSK_SIG_WSEL
+#define DSK_SIG_WSEL 0          // 0: re-read the winning group through a pointer; 1: select it from registers
+#endif
+#ifndef DSK_SIG_APPEND_NOINLINE
+#define DSK_SIG_APPEND_NOINLINE 1   // the long-document piece append as an out-of-line call
+#endif
+template <int P> constexpr bool kPend = DSK_SIG_PEND && P <= 4;
 
 template <int P, int OCC, bool PIECES>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
@@ -283,23 +303,32 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                 const int ngrp = (n_eff + 3) >> 2;   // 4-token groups holding at least one real token
 
                 // ---- phase 1: m = smallest key, m2 = second smallest, key = (block min L' & ~31) | block -------
-                uint32_t m[P], m2[P];
+                // kPend: the tracking ops of a block are folded in while the NEXT block's IMADs issue (pend = the previous
+                // block's key; 2^32-1 is a no-op), so that no run of 16 non-multiply instructions ends each block.
+                uint32_t m[P], m2[P], pend[kPend<P> ? P : 1];
 #pragma unroll
                 for (int j = 0; j < P; ++j) { m[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
-                // (Folding a block's four tracking ops in during the NEXT block's IMADs -- so that no run of 16 non-multiply
-                // instructions ends each block -- was measured: no gain, profiles/r2i_kernel_variants_ab.txt.)
+                if constexpr (kPend<P>) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) pend[j] = 0xFFFFFFFFu;
+                }
+                auto fold = [&](uint32_t key, int j) {
+                    const uint32_t om = m[j];
+                    m2[j] = min(m2[j], max(key, om));
+                    m[j] = min(om, key);
+                };
                 auto compute = [&](const uint32_t (&t)[16], uint32_t lb) {
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
                         const uint32_t c = c7[j];
                         uint32_t bm = umin3(alo[j] * t[0] + c, alo[j] * t[1] + c, alo[j] * t[2] + c);
+                        if constexpr (kPend<P>) fold(pend[j], j);
 #pragma unroll
                         for (int i = 3; i < 15; i += 2) bm = umin3(bm, alo[j] * t[i] + c, alo[j] * t[i + 1] + c);
                         bm = min(bm, alo[j] * t[15] + c);
                         const uint32_t key = (bm & ~kKeyMask) | lb;
-                        const uint32_t om = m[j];
-                        m2[j] = min(m2[j], max(key, om));
-                        m[j] = min(om, key);
+                        if constexpr (kPend<P>) pend[j] = key;
+                        else fold(key, j);
                     }
                 };
                 {
@@ -334,11 +363,15 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                     }
                 }
 
+                if constexpr (kPend<P>) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) fold(pend[j], j);   // the last block's key
+                }
+
                 // ---- phase 2: exact evaluation inside each permutation's winning block ------------------------
                 uint32_t res[P], win[P];   // win: upper end of the L' window the flagged path must evaluate
                 unsigned need_slow = 0;
-                // permutations handled together: 2 measured best for P <= 4, 4 for P = 8 (profiles/r2i_kernel_variants_ab.txt)
-                constexpr int G = P > 4 ? 4 : (P < 2 ? P : 2);
+                constexpr int G = P > 4 ? 4 : (P < DSK_SIG_G ? P : DSK_SIG_G);   // permutations handled together
 #pragma unroll
                 for (int j0 = 0; j0 < P; j0 += G) {
                     uint4 v[G][4];
@@ -348,7 +381,8 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[g][i] = wb[i];
                     }
-                    const uint4 *wsrc[G];   // the one group inside the window (re-read below: 5 ops instead of 12 selects)
+                    const uint4 *wsrc[G];   // the one group inside the window (DSK_SIG_WSEL 0: re-read below; 1: register selects)
+                    uint4 w[G];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const int j = j0 + g;
@@ -367,11 +401,13 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         // another block or another group inside the window, or L'-7 may wrap: the warp resolves it below
                         if (nin != 1 || m[j] <= kKeyMask || (m2[j] - m[j]) <= kNearWindow) need_slow |= 1u << j;
                         win[j] = (m[j] <= kKeyMask || thr < 7u) ? 0xFFFFFFFFu : thr;
-                        wsrc[g] = reinterpret_cast<const uint4 *>(src + (m[j] & kKeyMask) * 16u) + (in0 ? 0 : in1 ? 1 : in2 ? 2 : 3);
+                        if constexpr (DSK_SIG_WSEL) w[g] = in0 ? v[g][0] : in1 ? v[g][1] : in2 ? v[g][2] : v[g][3];
+                        else wsrc[g] = reinterpret_cast<const uint4 *>(src + (m[j] & kKeyMask) * 16u) + (in0 ? 0 : in1 ? 1 : in2 ? 2 : 3);
                     }
-                    uint4 w[G];
+                    if constexpr (!DSK_SIG_WSEL) {
 #pragma unroll
-                    for (int g = 0; g < G; ++g) w[g] = *wsrc[g];
+                        for (int g = 0; g < G; ++g) w[g] = *wsrc[g];
+                    }
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const int j = j0 + g;
