@@ -407,6 +407,39 @@ def run_ours(args):
                       "slowdown_vs_unique": ms_d / ms_step, "rows_verified": True}
         del d_dup, d_out2
 
+    # ---- 64-bit hash values: the same documents with a random high word on every token (minhash.py:294 accepts any hash
+    # below 2^64).  The signature kernel's general variant (low-word plane in phase 1, 64-bit form with the conditional
+    # subtract only in its exact stage) next to round 1's EXACT kernel, which evaluates the 64-bit form for every
+    # (token, permutation); rows spot-checked against the oracle.
+    u64_tokens = None
+    if not args.no_dups and args.kernel in ("auto", "two_phase"):
+        g = torch.Generator(device=dev).manual_seed(11 + rank)
+        d_tok64 = torch.randint(0, 1 << 32, (n * t,), device=dev, dtype=torch.int64, generator=g)
+        d_tok64.mul_(1 << 32).add_(d_tok.view(-1).to(torch.int64) & 0xFFFFFFFF)   # (hi << 32) | lo, as the bit pattern
+        d_out3 = torch.empty_like(d_out)
+        res = {}
+        for name, steps in (("two_phase", args.steps), ("exact", min(args.steps, 3))):
+            def step64():
+                dsk.engine.bulk_signatures_device(d_tok64, d_off, n * t, perms, d_out=d_out3, kernel=name, stream=stream.cuda_stream)
+            for _ in range(2):
+                step64()
+            barrier()
+            ev0.record(stream)
+            for _ in range(steps):
+                step64()
+            ev1.record(stream)
+            barrier()
+            res[name] = ev0.elapsed_time(ev1) / steps
+            sub64 = d_tok64.view(n, t)[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.uint64).reshape(-1)
+            want64 = oc.minhash_bulk_u64tok(np.ascontiguousarray(sub64), np.arange(len(idx) + 1, dtype=np.int64) * t, perms)
+            if not np.array_equal(d_out3[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.uint32), want64):
+                raise SystemExit("bench: signatures of the 64-bit-token documents (%s) differ from the oracle" % name)
+        u64_tokens = {"ms_per_step": res["two_phase"], "value": n / (res["two_phase"] * 1e-3), "unit": UNIT + " per GPU",
+                      "slowdown_vs_u32": res["two_phase"] / ms_step, "exact_kernel_ms_per_step": res["exact"],
+                      "speedup_vs_exact_kernel": res["exact"] / res["two_phase"], "rows_verified": True,
+                      "steps": {"two_phase": args.steps, "exact": min(args.steps, 3)}}
+        del d_tok64, d_out3
+
     # ---- e2e: pinned host buffers through the host C-ABI ------------------------------------------
     e2e = None
     e2e_launches = 0
@@ -621,7 +654,8 @@ def run_ours(args):
             "e2e": e2e, "clocks": clocks,
             # the two-phase path launches minhash_sig_kernel twice per device-resident step (documents, then the piece
             # table of long documents -- empty here, an idle launch); the host pipeline launches it once per slice
-            "gpu_launches": (2 if kern == "two_phase" else 1) * args.steps * (1 if duplicates is None else 2) + e2e_launches,
+            "gpu_launches": (2 if kern == "two_phase" else 1) * args.steps * (1 if duplicates is None else 2) + e2e_launches
+                            + (0 if u64_tokens is None else 2 * args.steps + min(args.steps, 3)),
         }
         # the roof that actually binds this kernel: one 32-bit IMAD per (token, permutation) evaluation is the floor
         # of any exact scheme, and B200 issues IMAD at 16 lanes/clk/SMSP = 64 lanes/clk/SM (profiles/)
@@ -639,6 +673,8 @@ def run_ours(args):
         line["strong"] = strong
         if duplicates is not None:
             line["duplicates"] = duplicates
+        if u64_tokens is not None:
+            line["u64_tokens"] = u64_tokens
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -104,7 +104,7 @@ struct dsk_perm {
     int num_perm = 0;
     int kpad = 0;
     int n_unsafe = 0;
-    uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi | b_lo + 7, each kpad entries
+    uint32_t *d_tab = nullptr;  // a_lo | a_hi | b_lo | b_hi | b_lo + 7 | b_lo + 8, each kpad entries
     unsigned *d_counters = nullptr;  // kCounterSets x kCounterStride work counters (one set per in-flight launch)
     // A launch leases one counter set; the event recorded behind the launch makes the NEXT user of that set wait
     // (stream-ordered, on the device) until the kernel that still reads it has finished -- 64+ launches of one handle
@@ -195,7 +195,7 @@ int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int 
     p->kpad = (num_perm + 255) / 256 * 256;
     p->a.assign(h_a, h_a + num_perm);
     p->b.assign(h_b, h_b + num_perm);
-    std::vector<uint32_t> tab((size_t)5 * p->kpad, 0u);
+    std::vector<uint32_t> tab((size_t)6 * p->kpad, 0u);
     for (int i = 0; i < num_perm; ++i) {
         tab[i] = (uint32_t)h_a[i];
         tab[p->kpad + i] = (uint32_t)(h_a[i] >> 32);
@@ -210,7 +210,10 @@ int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int 
         const int src = i % num_perm;
         for (int q = 0; q < 4; ++q) tab[(size_t)q * p->kpad + i] = tab[(size_t)q * p->kpad + src];
     }
-    for (int i = 0; i < p->kpad; ++i) tab[(size_t)4 * p->kpad + i] = tab[(size_t)2 * p->kpad + i] + 7u;
+    for (int i = 0; i < p->kpad; ++i) {
+        tab[(size_t)4 * p->kpad + i] = tab[(size_t)2 * p->kpad + i] + 7u;
+        tab[(size_t)5 * p->kpad + i] = tab[(size_t)2 * p->kpad + i] + 8u;
+    }
     int prev = 0;
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
@@ -265,17 +268,20 @@ void dsk_perm_destroy(dsk_perm *p) {
 }
 
 static int pick_mode(const dsk_perm *perm, int token_is_u64, int flags, int *mode) {
+    // The two-phase kernel has a variant for every input (BulkParams::gen): the default one needs 32-bit tokens and
+    // permutations that cannot reach the conditional subtract of `% (2^61-1)`; the general ones take the subtract in their
+    // exact stage (window 8 instead of 7).  DIRECT evaluates r = lo32(x) + top3(x) everywhere and keeps that requirement.
     const bool fast_ok = !token_is_u64 && perm->n_unsafe == 0;
     switch (flags) {
-        case DSK_KERNEL_AUTO: *mode = fast_ok ? MODE_TWO_PHASE : MODE_EXACT; return DSK_OK;
-        case DSK_KERNEL_TWO_PHASE:
+        case DSK_KERNEL_AUTO:
+        case DSK_KERNEL_TWO_PHASE: *mode = MODE_TWO_PHASE; return DSK_OK;
         case DSK_KERNEL_DIRECT:
             if (!fast_ok) {
-                set_error("fast kernels are not exact here (token_is_u64=%d, unsafe permutations=%d); use DSK_KERNEL_EXACT/AUTO",
+                set_error("DSK_KERNEL_DIRECT is not exact here (token_is_u64=%d, unsafe permutations=%d); use DSK_KERNEL_AUTO / TWO_PHASE / EXACT",
                           token_is_u64, perm->n_unsafe);
                 return DSK_ERR_INVALID;
             }
-            *mode = (flags == DSK_KERNEL_TWO_PHASE) ? MODE_TWO_PHASE : MODE_DIRECT;
+            *mode = MODE_DIRECT;
             return DSK_OK;
         case DSK_KERNEL_EXACT: *mode = MODE_EXACT; return DSK_OK;
         default: set_error("unknown kernel flag %d", flags); return DSK_ERR_INVALID;
@@ -331,6 +337,8 @@ int dsk_minhash_bulk_ws(const dsk_perm *perm, const void *d_tokens, int token_is
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
     prm.b_hi = perm->d_tab + 3 * perm->kpad;
     prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
+    prm.b_lo8 = perm->d_tab + 5 * perm->kpad;
+    prm.gen = token_is_u64 ? 2 : (perm->n_unsafe ? 1 : 0);
     prm.k = perm->num_perm;
     prm.init = d_init;
     prm.init_stride = init_stride;
@@ -381,6 +389,8 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
     prm.b_hi = perm->d_tab + 3 * perm->kpad;
     prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
+    prm.b_lo8 = perm->d_tab + 5 * perm->kpad;
+    prm.gen = token_is_u64 ? 2 : (perm->n_unsafe ? 1 : 0);
     prm.k = perm->num_perm;
     prm.init = nullptr;
     prm.init_stride = 0;
@@ -1077,6 +1087,8 @@ int dsk_minhash_bulk_host(const dsk_perm *perm, const void *h_tokens, int token_
     prm.b_lo = perm->d_tab + 2 * perm->kpad;
     prm.b_hi = perm->d_tab + 3 * perm->kpad;
     prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
+    prm.b_lo8 = perm->d_tab + 5 * perm->kpad;
+    prm.gen = token_is_u64 ? 2 : (perm->n_unsafe ? 1 : 0);
     prm.k = K;
     prm.init = nullptr;
     prm.init_stride = init_stride;

@@ -63,6 +63,9 @@ struct BulkParams {
     int piece_shift;            // log2 of the piece length in tokens
     unsigned *piece_hdr;        // [0] = pieces appended so far; [64 + K-slice] = work counters of the piece-mode launch
     struct PieceDesc *pieces;   // capacity guaranteed by the caller: n_tokens / 2^piece_shift + n_tokens / long_doc_tokens + 2
+    // general variants of the signature kernel (appended last: the layout the default variant sees stays as it was)
+    const uint32_t *b_lo8;      // b_lo + 8: the addend of L' when `% p` may take its conditional subtract (window 8)
+    int gen;                    // 0 = u32 tokens + safe permutations, 1 = u32 tokens + any permutations, 2 = u64 tokens
 };
 struct PieceDesc { int64_t row, start, end, reserved; };
 constexpr int kPieceHdrBytes = 512;
@@ -70,7 +73,7 @@ constexpr int64_t kLongDocTokensApi = 4096;   // documents longer than this are 
 constexpr int kPieceShiftApi = 10;
 enum { MODE_TWO_PHASE = 0, MODE_DIRECT = 1, MODE_EXACT = 2 };
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s);
-cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s);   // signature_kernel.cu (two-phase)
+cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s);   // signature_kernel.cu (two-phase; variant = prm.gen)
 size_t minhash_sig_workspace_bytes(int64_t n_tokens);   // piece table for long documents (0 if none can occur)
 cudaError_t launch_seg_min(const uint32_t *part, const int64_t *seg, int64_t n_docs, int k, const void *init,
                            int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int sm_count,

@@ -540,13 +540,14 @@ static cudaError_t launch_bulk_p(const BulkParams &prm, int sm_count, cudaStream
 }
 
 cudaError_t launch_minhash_bulk(const BulkParams &prm, int mode, int token_is_u64, int sm_count, cudaStream_t s) {
-    if (token_is_u64) return launch_bulk_p<MODE_EXACT, uint64_t>(prm, sm_count, s);
-    switch (mode) {
-        case MODE_TWO_PHASE:
-            return two_phase_v1() ? launch_bulk_p<MODE_TWO_PHASE, uint32_t>(prm, sm_count, s) : launch_minhash_sig(prm, sm_count, s);
-        case MODE_DIRECT: return launch_bulk_p<MODE_DIRECT, uint32_t>(prm, sm_count, s);
-        default: return launch_bulk_p<MODE_EXACT, uint32_t>(prm, sm_count, s);
+    if (mode == MODE_TWO_PHASE) {   // signature_kernel.cu: prm.gen names the variant (u32 safe / u32 any permutation / u64 tokens)
+        if (prm.gen == 0 && !token_is_u64 && two_phase_v1()) return launch_bulk_p<MODE_TWO_PHASE, uint32_t>(prm, sm_count, s);
+        if ((prm.gen == 2) != (token_is_u64 != 0)) return cudaErrorInvalidValue;
+        return launch_minhash_sig(prm, sm_count, s);
     }
+    if (token_is_u64) return launch_bulk_p<MODE_EXACT, uint64_t>(prm, sm_count, s);
+    if (mode == MODE_DIRECT) return launch_bulk_p<MODE_DIRECT, uint32_t>(prm, sm_count, s);
+    return launch_bulk_p<MODE_EXACT, uint32_t>(prm, sm_count, s);
 }
 
 cudaError_t launch_sig_merge_min(const uint32_t *x, const uint32_t *y, int64_t n, uint32_t *out, int sm_count,

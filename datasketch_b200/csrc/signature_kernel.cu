@@ -24,6 +24,12 @@
 //   long     with a caller-provided piece table (dsk_minhash_bulk_ws) a document longer than 4096 tokens is not processed
 //            where it is met: its row gets the initial value and ceil(len / 1024) piece descriptors are appended; a
 //            second launch (template flag PIECES) spreads the pieces over all warps and min-merges with atomicMin.
+//   general  (template GEN) the same kernel for inputs the formula above does not cover.  For ANY 64-bit x,
+//            (x mod p) & (2^32-1) = lo32(x) + top3(x) + s  (mod 2^32),  s = 1 iff `% p` takes its conditional subtract
+//            ((x & p) + top3(x) >= p; -p = +1 mod 2^32), so r lies in [L'-8, L'] with L' = lo32(a_lo*h_lo + b_lo + 8): phase 1 is
+//            unchanged (one IMAD on the LOW words) and only the exact stage evaluates the 64-bit form.  GEN = 1: u32 tokens
+//            with permutations that can reach the subtract (user-supplied ones); GEN = 2: u64 tokens (hash values up to
+//            2^64-1, minhash.py:294) -- staged as a low-word plane (phase 1) and a high-word plane (exact stage only).
 //   flagged  a permutation with another block inside the window (m2 - m <= 69), a second group inside the window,
 //            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp, two permutations
 //            at a time: every lane filters 1/32 of the sub-piece's tokens with L' and evaluates r exactly for the
@@ -43,7 +49,9 @@ constexpr int kSubTok = 512;        // tokens per sub-piece
 constexpr int kTabSlots = 1024;     // de-duplication table: one slot per hashed token value, later tokens overwrite earlier ones
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kKeyMask = 31u;  // low bits of a tracking key hold the block index (32 blocks of 16 tokens)
-constexpr uint32_t kNearWindow = 7u + 2u * kKeyMask;  // m2 - m <= this: another block may be inside the +7 window
+template <int GEN> constexpr uint32_t kWin = GEN ? 8u : 7u;          // r lies in [L' - kWin, L']
+template <int GEN> constexpr uint32_t kNearWindow = kWin<GEN> + 2u * kKeyMask;  // m2 - m <= this: another block may be inside the window
+constexpr int kHiOff = kSubTok / 2;  // GEN = 2: high words of a staged sub-piece (<= 256 tokens) live at buf[kHiOff + i]
 constexpr int kDedupeOnFlags = 8;   // flagged permutations in one sub-piece (of 32*P) that switch de-duplication on
 
 // Path counters for the CPU emulation tests (tests/emu): which staging path / how many flagged permutations.
@@ -64,6 +72,16 @@ __device__ __forceinline__ uint32_t sig_eval(uint32_t alo, uint32_t ahi, uint64_
     uint64_t x = (uint64_t)alo * h + b;                     // IMAD.WIDE.U32
     uint32_t xh = (uint32_t)(x >> 32) + ahi * h;            // IMAD
     return (uint32_t)x + (xh >> 29);                        // LEA.HI
+}
+
+// any x: r = ((x mod 2^64) % (2^61-1)) & (2^32-1) with 64-bit tokens and the conditional subtract (general variants)
+__device__ __forceinline__ uint32_t sig_eval_gen(uint32_t alo, uint32_t ahi, uint64_t b, uint32_t hlo, uint32_t hhi) {
+    const uint64_t a = ((uint64_t)ahi << 32) | alo, h = ((uint64_t)hhi << 32) | hlo;
+    const uint64_t x = a * h + b;
+    const uint64_t p = (1ull << 61) - 1;
+    uint64_t y = (x & p) + (x >> 61);
+    if (y >= p) y -= p;
+    return (uint32_t)y;
 }
 
 __device__ __forceinline__ void load_block16(const uint32_t *src, uint32_t (&t)[16]) {
@@ -115,8 +133,11 @@ void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int6
 #endif
 template <int P> constexpr bool kPend = DSK_SIG_PEND && P <= 4;
 
-template <int P, int OCC, bool PIECES>
+template <int P, int OCC, bool PIECES, int GEN>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
+    constexpr int TW = GEN == 2 ? 2 : 1;            // 32-bit words per token; the ring and its copies count WORDS
+    constexpr int SUB = GEN == 2 ? kHiOff : kSubTok;  // tokens per sub-piece
+    constexpr uint32_t W = kWin<GEN>;
     __shared__ __align__(128) uint32_t s_ring[kSigWarps][kRingTok];
     __shared__ __align__(128) uint32_t s_buf[kSigWarps][kSubTok];
     __shared__ __align__(16) uint32_t s_tab[kSigWarps][kTabSlots];
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
     for (int j = 0; j < P; ++j) {
         alo[j] = __ldg(prm.a_lo + kl + j); ahi[j] = __ldg(prm.a_hi + kl + j);
         // the table holds b_lo + 7 as its own plane: computed here, ptxas re-adds the 7 in every loop iteration
-        c7[j] = __ldg(prm.b_lo7 + kl + j); bhi[j] = __ldg(prm.b_hi + kl + j);
+        c7[j] = __ldg((GEN ? prm.b_lo8 : prm.b_lo7) + kl + j); bhi[j] = __ldg(prm.b_hi + kl + j);   // c7 = b_lo + W
     }
 
     uint32_t *const ring = s_ring[warp];
@@ -155,8 +176,9 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
     uint32_t par_mask = 0;  // bit s = phase parity the next wait on slot s must use
 
     // bulk copies move 16-byte granules: the last (n_tokens mod 4) tokens of the array are patched in by lanes
-    const int64_t copy_end_tok = n_tokens & ~(int64_t)3;
-    const int64_t tail_chunk = (copy_end_tok < n_tokens) ? (copy_end_tok >> kChunkShift) : -1;
+    const int64_t n_words = n_tokens * TW;
+    const int64_t copy_end_tok = n_words & ~(int64_t)3;
+    const int64_t tail_chunk = (copy_end_tok < n_words) ? (copy_end_tok >> kChunkShift) : -1;
 
     bool dedupe = false;     // warp-uniform: copy stage removes repeated tokens
     int clean_run = 0;       // consecutive deduplicated sub-pieces in which nothing was removed
@@ -175,9 +197,10 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
         } else {
             tok_lo = __ldg(offsets + dlo); tok_hi = __ldg(offsets + dhi);
         }
-        int64_t c_next = tok_lo >> kChunkShift;                 // next chunk to issue
+        // ring positions below are WORD positions (= token positions unless tokens are 64-bit)
+        int64_t c_next = (tok_lo * TW) >> kChunkShift;          // next chunk to issue
         int64_t c_wait = c_next;                                // next chunk to wait for
-        const int64_t c_last = (tok_hi - 1) >> kChunkShift;     // last chunk this unit touches (if it has tokens)
+        const int64_t c_last = (tok_hi * TW - 1) >> kChunkShift;  // last chunk this unit touches (if it has tokens)
 
         // consume the completions of copies that were issued for chunks < upto but never needed (skipped tokens): every
         // issued copy must be waited for exactly once, or the slot's phase parity goes out of step
@@ -223,7 +246,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                 par_mask ^= 1u << slot;
                 if (c_wait == tail_chunk) {     // the < 16-byte tail of the whole array cannot travel by bulk copy
                     const int64_t g = copy_end_tok + lane;
-                    if (g < n_tokens) ring[g & (kRingTok - 1)] = __ldg(tokens + g);
+                    if (g < n_words) ring[g & (kRingTok - 1)] = __ldg(tokens + g);
                     fence_proxy_async();        // generic-proxy write, later bulk copies reuse the slot
                     __syncwarp();
                 }
@@ -248,22 +271,30 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                 if (defer && blockIdx.y == 0) append_pieces(prm.piece_hdr, prm.pieces, prm.piece_shift, d, start, end, lane);
             }
 
-            for (int64_t s = start; s < (defer ? start : end); s += kSubTok) {
-                const int len = (int)min((int64_t)kSubTok, end - s);
-                ensure(s, s + len);
-                const uint32_t rpos = (uint32_t)s & (kRingTok - 1);
+            for (int64_t s = start; s < (defer ? start : end); s += SUB) {
+                const int len = (int)min((int64_t)SUB, end - s);
+                ensure(s * TW, (s + len) * TW);
+                const uint32_t rpos = (uint32_t)(s * TW) & (kRingTok - 1);
 
                 // ---- stage: in place, or copy / re-align / pad / deduplicate into the line buffer ----------------
                 const uint32_t *src;
                 int n_eff = len;
-                const bool in_place = !dedupe && (len & 15) == 0 && (rpos & 3u) == 0 && rpos + (uint32_t)len <= (uint32_t)kRingTok;
+                const bool in_place = TW == 1 && !dedupe && (len & 15) == 0 && (rpos & 3u) == 0 && rpos + (uint32_t)len <= (uint32_t)kRingTok;
                 if (in_place) {
                     src = ring + rpos;
                     DSK_SIG_STAT(STAT_IN_PLACE, 1);
                 } else {
                     __syncwarp();   // every lane is done with the previous contents of buf / tab
                     if (!dedupe) {
-                        for (int i = lane; i < len; i += 32) buf[i] = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
+                        if constexpr (TW == 2) {   // de-interleave: low words -> buf[i] (phase 1), high words -> buf[kHiOff + i]
+                            const uint2 *r2 = reinterpret_cast<const uint2 *>(ring);
+                            for (int i = lane; i < len; i += 32) {
+                                const uint2 t = r2[((rpos >> 1) + (uint32_t)i) & (kRingTok / 2 - 1)];
+                                buf[i] = t.x; buf[kHiOff + i] = t.y;
+                            }
+                        } else {
+                            for (int i = lane; i < len; i += 32) buf[i] = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
+                        }
                         DSK_SIG_STAT(STAT_COPIED, 1);
                     } else {
                         uint4 *t4 = reinterpret_cast<uint4 *>(tab);
@@ -279,11 +310,23 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         for (int i0 = 0; i0 < len; i0 += 32) {
                             const int i = i0 + lane;
                             bool keep = i < len;
-                            uint32_t t = kEmptySlot;
-                            if (keep) t = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
-                            if (t != kEmptySlot) keep = atomicExch(&tab[(t * 0x9E3779B1u) >> 22], t) != t;
+                            uint32_t t = kEmptySlot, thi = kEmptySlot;
+                            if constexpr (TW == 2) {   // the same table as 512 64-bit slots; identity = the whole 64-bit token
+                                if (keep) {
+                                    const uint2 t2 = reinterpret_cast<const uint2 *>(ring)[((rpos >> 1) + (uint32_t)i) & (kRingTok / 2 - 1)];
+                                    t = t2.x; thi = t2.y;
+                                }
+                                const unsigned long long t64 = ((unsigned long long)thi << 32) | t;
+                                if (t64 != ~0ull)
+                                    keep = atomicExch(reinterpret_cast<unsigned long long *>(tab) + (((t ^ (thi * 0x85EBCA6Bu)) * 0x9E3779B1u) >> 23), t64) != t64;
+                            } else {
+                                if (keep) t = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
+                                if (t != kEmptySlot) keep = atomicExch(&tab[(t * 0x9E3779B1u) >> 22], t) != t;
+                            }
                             const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-                            if (keep) buf[base + __popc(bal & ((1u << lane) - 1u))] = t;
+                            const int at = base + __popc(bal & ((1u << lane) - 1u));
+                            if (keep) buf[at] = t;
+                            if constexpr (TW == 2) { if (keep) buf[kHiOff + at] = thi; }
                             base += __popc(bal);
                         }
                         n_eff = base;
@@ -294,8 +337,13 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         __syncwarp();   // buf[n_eff - 1] below was written by another lane
                     }
                     const int pad = (16 - (n_eff & 15)) & 15;
-                    if (lane < pad) buf[n_eff + lane] = dedupe || n_eff != len ? buf[n_eff - 1]
-                                                                               : ring[(rpos + (uint32_t)len - 1u) & (kRingTok - 1)];
+                    if constexpr (TW == 2) {
+                        __syncwarp();   // buf[n_eff - 1] was written by another lane
+                        if (lane < pad) { buf[n_eff + lane] = buf[n_eff - 1]; buf[kHiOff + n_eff + lane] = buf[kHiOff + n_eff - 1]; }
+                    } else {
+                        if (lane < pad) buf[n_eff + lane] = dedupe || n_eff != len ? buf[n_eff - 1]
+                                                                                   : ring[(rpos + (uint32_t)len - 1u) & (kRingTok - 1)];
+                    }
                     __syncwarp();
                     src = buf;
                 }
@@ -392,28 +440,35 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                         for (int i = 0; i < 4; ++i)
                             gm[i] = min(umin3(alo[j] * v[g][i].x + c, alo[j] * v[g][i].y + c, alo[j] * v[g][i].z + c),
                                         alo[j] * v[g][i].w + c);
-                        const uint32_t thr = min(umin3(gm[0], gm[1], gm[2]), gm[3]) + 7u;   // a wrap implies m2 - m <= window
+                        const uint32_t thr = min(umin3(gm[0], gm[1], gm[2]), gm[3]) + W;   // a wrap implies m2 - m <= window
                         // groups made of padding only (last block) repeat a real token: they never count as a second group
                         const int gv = ngrp - (int)(m[j] & kKeyMask) * 4;
                         const bool in0 = gm[0] <= thr, in1 = gm[1] <= thr && gv > 1, in2 = gm[2] <= thr && gv > 2,
                                    in3 = gm[3] <= thr && gv > 3;
                         const int nin = (int)in0 + (int)in1 + (int)in2 + (int)in3;
                         // another block or another group inside the window, or L'-7 may wrap: the warp resolves it below
-                        if (nin != 1 || m[j] <= kKeyMask || (m2[j] - m[j]) <= kNearWindow) need_slow |= 1u << j;
-                        win[j] = (m[j] <= kKeyMask || thr < 7u) ? 0xFFFFFFFFu : thr;
-                        if constexpr (DSK_SIG_WSEL) w[g] = in0 ? v[g][0] : in1 ? v[g][1] : in2 ? v[g][2] : v[g][3];
+                        if (nin != 1 || m[j] <= kKeyMask || (m2[j] - m[j]) <= kNearWindow<GEN>) need_slow |= 1u << j;
+                        win[j] = (m[j] <= kKeyMask || thr < W) ? 0xFFFFFFFFu : thr;
+                        if constexpr (DSK_SIG_WSEL && GEN != 2) w[g] = in0 ? v[g][0] : in1 ? v[g][1] : in2 ? v[g][2] : v[g][3];
                         else wsrc[g] = reinterpret_cast<const uint4 *>(src + (m[j] & kKeyMask) * 16u) + (in0 ? 0 : in1 ? 1 : in2 ? 2 : 3);
                     }
-                    if constexpr (!DSK_SIG_WSEL) {
+                    if constexpr (!DSK_SIG_WSEL || GEN == 2) {
 #pragma unroll
                         for (int g = 0; g < G; ++g) w[g] = *wsrc[g];
                     }
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const int j = j0 + g;
-                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | (c7[j] - 7u);
-                        res[j] = min(umin3(sig_eval(alo[j], ahi[j], b64, w[g].x), sig_eval(alo[j], ahi[j], b64, w[g].y),
-                                           sig_eval(alo[j], ahi[j], b64, w[g].z)), sig_eval(alo[j], ahi[j], b64, w[g].w));
+                        const uint64_t b64 = ((uint64_t)bhi[j] << 32) | (c7[j] - W);
+                        if constexpr (GEN) {   // full `% p` (conditional subtract); GEN = 2: the group's high words from the second plane
+                            uint4 wh = make_uint4(0u, 0u, 0u, 0u);
+                            if constexpr (GEN == 2) wh = wsrc[g][kHiOff / 4];
+                            res[j] = min(umin3(sig_eval_gen(alo[j], ahi[j], b64, w[g].x, wh.x), sig_eval_gen(alo[j], ahi[j], b64, w[g].y, wh.y),
+                                               sig_eval_gen(alo[j], ahi[j], b64, w[g].z, wh.z)), sig_eval_gen(alo[j], ahi[j], b64, w[g].w, wh.w));
+                        } else {
+                            res[j] = min(umin3(sig_eval(alo[j], ahi[j], b64, w[g].x), sig_eval(alo[j], ahi[j], b64, w[g].y),
+                                               sig_eval(alo[j], ahi[j], b64, w[g].z)), sig_eval(alo[j], ahi[j], b64, w[g].w));
+                        }
                     }
                 }
 
@@ -438,15 +493,21 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                             const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, c7[j], o0), c1 = __shfl_sync(0xFFFFFFFFu, c7[j], o1);
                             const uint32_t g0 = __shfl_sync(0xFFFFFFFFu, bhi[j], o0), g1 = __shfl_sync(0xFFFFFFFFu, bhi[j], o1);
                             const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, win[j], o0), w1 = __shfl_sync(0xFFFFFFFFu, win[j], o1);
-                            const uint64_t b0 = ((uint64_t)g0 << 32) | (c0 - 7u), b1 = ((uint64_t)g1 << 32) | (c1 - 7u);
+                            const uint64_t b0 = ((uint64_t)g0 << 32) | (c0 - W), b1 = ((uint64_t)g1 << 32) | (c1 - W);
                             uint32_t r0 = 0xFFFFFFFFu, r1 = 0xFFFFFFFFu;
 #pragma unroll 4
                             for (int i = lane; i < n_pad; i += 32) {
                                 const uint32_t t = src[i];
                                 const bool k0 = a0 * t + c0 <= w0, k1 = a1 * t + c1 <= w1;
                                 if (k0 || k1) {
-                                    if (k0) r0 = min(r0, sig_eval(a0, h0, b0, t));
-                                    if (k1) r1 = min(r1, sig_eval(a1, h1, b1, t));
+                                    if constexpr (GEN) {
+                                        const uint32_t thi = GEN == 2 ? src[kHiOff + i] : 0u;
+                                        if (k0) r0 = min(r0, sig_eval_gen(a0, h0, b0, t, thi));
+                                        if (k1) r1 = min(r1, sig_eval_gen(a1, h1, b1, t, thi));
+                                    } else {
+                                        if (k0) r0 = min(r0, sig_eval(a0, h0, b0, t));
+                                        if (k1) r1 = min(r1, sig_eval(a1, h1, b1, t));
+                                    }
                                 }
                             }
                             r0 = __reduce_min_sync(0xFFFFFFFFu, r0);
@@ -536,7 +597,7 @@ size_t minhash_sig_workspace_bytes(int64_t n_tokens) {
     return (size_t)kPieceHdrBytes + (size_t)cap * sizeof(PieceDesc);
 }
 
-template <int P, int OCC>
+template <int P, int OCC, int GEN>
 static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
     BulkParams prm = prm_in;
     const int slices = (prm.k + 32 * P - 1) / (32 * P);
@@ -560,24 +621,34 @@ static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream
         if (e != cudaSuccess) return e;
     }
     dim3 grid((unsigned)gx, (unsigned)slices);
-    DSK_LAUNCH((minhash_sig_kernel<P, OCC, false>), grid, kSigWarps * 32, 0, s, prm);
+    DSK_LAUNCH((minhash_sig_kernel<P, OCC, false, GEN>), grid, kSigWarps * 32, 0, s, prm);
     e = cudaGetLastError();
     if (e != cudaSuccess || !split) return e;
     // second launch: the pieces (their number is only known on the device; an empty table costs one idle launch)
     dim3 pgrid((unsigned)gmax, (unsigned)slices);
-    DSK_LAUNCH((minhash_sig_kernel<P, OCC, true>), pgrid, kSigWarps * 32, 0, s, prm);
+    DSK_LAUNCH((minhash_sig_kernel<P, OCC, true, GEN>), pgrid, kSigWarps * 32, 0, s, prm);
     return cudaGetLastError();
+}
+
+template <int GEN>
+static cudaError_t launch_sig_k(const BulkParams &prm, int sm_count, cudaStream_t s) {
+    if (prm.k <= 32) return launch_sig<1, 4, GEN>(prm, sm_count, s);
+    if (prm.k <= 64) return launch_sig<2, 4, GEN>(prm, sm_count, s);
+    if (prm.k <= 128) return launch_sig<4, 4, GEN>(prm, sm_count, s);
+    // K > 128: 8 permutations per lane, or (DSK_SIG_WIDE=4, an A/B switch) K-slices of 128 on blockIdx.y with 4 per lane
+    static const bool wide4 = [] { const char *e = getenv("DSK_SIG_WIDE"); return e && atoi(e) == 4; }();
+    if (wide4) return launch_sig<4, 4, GEN>(prm, sm_count, s);
+    return launch_sig<8, 4, GEN>(prm, sm_count, s);
 }
 
 // 4 CTAs (16 warps) per SM: 5 and 6 were measured slower (register cap, profiles/r2i_kernel_variants_ab.txt)
 cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s) {
-    if (prm.k <= 32) return launch_sig<1, 4>(prm, sm_count, s);
-    if (prm.k <= 64) return launch_sig<2, 4>(prm, sm_count, s);
-    if (prm.k <= 128) return launch_sig<4, 4>(prm, sm_count, s);
-    // K > 128: 8 permutations per lane, or (DSK_SIG_WIDE=4, an A/B switch) K-slices of 128 on blockIdx.y with 4 per lane
-    static const bool wide4 = [] { const char *e = getenv("DSK_SIG_WIDE"); return e && atoi(e) == 4; }();
-    if (wide4) return launch_sig<4, 4>(prm, sm_count, s);
-    return launch_sig<8, 4>(prm, sm_count, s);
+    switch (prm.gen) {
+        case 0: return launch_sig_k<0>(prm, sm_count, s);
+        case 1: return launch_sig_k<1>(prm, sm_count, s);
+        case 2: return launch_sig_k<2>(prm, sm_count, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace dsk

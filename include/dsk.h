@@ -46,10 +46,13 @@ enum {
 
 /* kernel selection for dsk_minhash_bulk (flags) */
 enum {
-    DSK_KERNEL_AUTO = 0,     /* two-phase kernel when it is exact for (perm, token width), else exact */
-    DSK_KERNEL_TWO_PHASE = 1,/* force; returns DSK_ERR_INVALID if not exact for this handle / token width */
-    DSK_KERNEL_DIRECT = 2,   /* one full evaluation per (token, perm), no candidate filtering */
-    DSK_KERNEL_EXACT = 3     /* full 64-bit `% (2^61-1)` per evaluation; any permutation, u32/u64 tokens */
+    DSK_KERNEL_AUTO = 0,     /* = TWO_PHASE */
+    DSK_KERNEL_TWO_PHASE = 1,/* the two-phase signature kernel; bit-exact for ANY permutation and u32 / u64 tokens: the default
+                                variant needs 32-bit tokens and n_unsafe == 0, otherwise a general variant runs that
+                                takes the conditional subtract of `% (2^61-1)` in its exact stage (window 8 instead of 7) */
+    DSK_KERNEL_DIRECT = 2,   /* r = lo32(x) + top3(x) per (token, perm), no candidate filtering; DSK_ERR_INVALID unless
+                                the tokens are 32-bit and n_unsafe == 0 */
+    DSK_KERNEL_EXACT = 3     /* full 64-bit `% (2^61-1)` per evaluation; any permutation, u32/u64 tokens (round 1's kernel) */
 };
 
 DSK_API int dsk_version(void);
@@ -65,8 +68,9 @@ DSK_API int dsk_device_info(int device, int *sm_count, int *cc_major, int *cc_mi
  * (datasketch/minhash.py:170-184; generated on the HOST with numpy, never on
  * device) and analyses them once: `n_unsafe` = number of permutations for which
  * some 32-bit token value h makes ((a*h+b) mod 2^64) fall in the 36-value set
- * where `% (2^61-1)` needs its conditional subtract.  The two-phase / direct
- * kernels are bit-exact iff n_unsafe == 0 (otherwise AUTO picks the exact kernel).
+ * where `% (2^61-1)` needs its conditional subtract.  n_unsafe == 0 (true for every seed-generated
+ * set tested) selects the two-phase kernel's default variant and allows DSK_KERNEL_DIRECT; otherwise the
+ * two-phase kernel's general variant runs (same speed class, still bit-exact).
  * Replaces minhash.py:160-165 (_ensure_gpu_caches). */
 typedef struct dsk_perm dsk_perm;
 DSK_API int dsk_perm_create(const uint64_t *h_a, const uint64_t *h_b, int num_perm, int device, dsk_perm **out);

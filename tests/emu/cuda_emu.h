@@ -93,10 +93,11 @@ static inline unsigned long long atomicMin(unsigned long long *p, unsigned long 
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
 static inline unsigned atomicExch(unsigned *p, unsigned val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
 static inline int atomicExch(int *p, int val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
+static inline unsigned long long atomicExch(unsigned long long *p, unsigned long long val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- CUDA runtime, synchronous and on host memory: "device" pointers are host pointers, one fake device with two SMs
-enum { cudaErrorMemoryAllocation = 2, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100 };
+enum { cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100 };
 enum { cudaStreamNonBlocking = 1 };
 struct cudaDeviceProp { int multiProcessorCount, major, minor; size_t totalGlobalMem; char name[64]; };
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }

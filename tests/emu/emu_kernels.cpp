@@ -27,24 +27,26 @@ thread_local EmuCta *emu_cta = nullptr;
 extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
                                 const uint64_t *a, const uint64_t *b, int k, int mode, int v1,
                                 const void *init, int64_t init_stride, int init_is_u64, void *out, int out_is_u64,
-                                int docs_per_unit, int grid_x) {
+                                int docs_per_unit, int grid_x, int gen) {
     const int P = k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 8;
     const int kpad = (k + 255) / 256 * 256;
-    std::vector<uint32_t> tab((size_t)5 * kpad);
+    std::vector<uint32_t> tab((size_t)6 * kpad);
     for (int i = 0; i < kpad; ++i) {  // padding slots repeat real permutations, like dsk_perm_create
         const int s = i % k;
         tab[i] = (uint32_t)a[s]; tab[kpad + i] = (uint32_t)(a[s] >> 32);
         tab[2 * kpad + i] = (uint32_t)b[s]; tab[3 * kpad + i] = (uint32_t)(b[s] >> 32);
-        tab[4 * kpad + i] = (uint32_t)b[s] + 7u;
+        tab[4 * kpad + i] = (uint32_t)b[s] + 7u; tab[5 * kpad + i] = (uint32_t)b[s] + 8u;
     }
     std::vector<unsigned> counters(64, 0u);
     dsk::BulkParams prm{};
     prm.tokens = tokens; prm.offsets = offsets; prm.n_docs = n_docs; prm.n_tokens = offsets[n_docs];
     prm.a_lo = tab.data(); prm.a_hi = tab.data() + kpad; prm.b_lo = tab.data() + 2 * kpad; prm.b_hi = tab.data() + 3 * kpad; prm.b_lo7 = tab.data() + 4 * kpad;
+    prm.b_lo8 = tab.data() + 5 * kpad;
+    prm.gen = token_is_u64 ? 2 : gen;   // gen = 1: the general u32 variant (the API picks it when a permutation is unsafe)
     prm.k = k; prm.init = init; prm.init_stride = init_stride; prm.init_is_u64 = init_is_u64;
     prm.out = out; prm.out_is_u64 = out_is_u64; prm.work_counter = counters.data();
     prm.docs_per_unit = docs_per_unit; prm.n_peers = 0; prm.peer_row_offset = 0;
-    if (token_is_u64 && mode != dsk::MODE_EXACT) return -1;
+    if (token_is_u64 && mode == dsk::MODE_DIRECT) return -1;
     if (v1 && mode == dsk::MODE_TWO_PHASE) {
         switch (P) {
             case 1: return dsk::launch_bulk<1, dsk::MODE_TWO_PHASE, uint32_t, 4>(prm, grid_x, nullptr);
@@ -57,17 +59,17 @@ extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int6
 }
 
 // the signature kernel with the long-document piece table (thresholds chosen by the test, e.g. 100 / 32 tokens)
-extern "C" int emu_minhash_sig_long(const uint32_t *tokens, const int64_t *offsets, int64_t n_docs, const uint64_t *a,
+extern "C" int emu_minhash_sig_long(const void *tokens, const int64_t *offsets, int64_t n_docs, const uint64_t *a,
                                     const uint64_t *b, int k, const void *init, int64_t init_stride, int init_is_u64,
                                     void *out, int out_is_u64, int docs_per_unit, int grid_x, int64_t long_doc_tokens,
-                                    int piece_shift, long long *n_pieces_out) {
+                                    int piece_shift, long long *n_pieces_out, int gen) {
     const int kpad = (k + 255) / 256 * 256;
-    std::vector<uint32_t> tab((size_t)5 * kpad);
+    std::vector<uint32_t> tab((size_t)6 * kpad);
     for (int i = 0; i < kpad; ++i) {
         const int s = i % k;
         tab[i] = (uint32_t)a[s]; tab[kpad + i] = (uint32_t)(a[s] >> 32);
         tab[2 * kpad + i] = (uint32_t)b[s]; tab[3 * kpad + i] = (uint32_t)(b[s] >> 32);
-        tab[4 * kpad + i] = (uint32_t)b[s] + 7u;
+        tab[4 * kpad + i] = (uint32_t)b[s] + 7u; tab[5 * kpad + i] = (uint32_t)b[s] + 8u;
     }
     std::vector<unsigned> counters(64, 0u);
     const int64_t n_tokens = offsets[n_docs];
@@ -77,7 +79,7 @@ extern "C" int emu_minhash_sig_long(const uint32_t *tokens, const int64_t *offse
     dsk::BulkParams prm{};
     prm.tokens = tokens; prm.offsets = offsets; prm.n_docs = n_docs; prm.n_tokens = n_tokens;
     prm.a_lo = tab.data(); prm.a_hi = tab.data() + kpad; prm.b_lo = tab.data() + 2 * kpad; prm.b_hi = tab.data() + 3 * kpad;
-    prm.b_lo7 = tab.data() + 4 * kpad;
+    prm.b_lo7 = tab.data() + 4 * kpad; prm.b_lo8 = tab.data() + 5 * kpad; prm.gen = gen;
     prm.k = k; prm.init = init; prm.init_stride = init_stride; prm.init_is_u64 = init_is_u64;
     prm.out = out; prm.out_is_u64 = out_is_u64; prm.work_counter = counters.data();
     prm.docs_per_unit = docs_per_unit;

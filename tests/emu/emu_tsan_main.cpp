@@ -23,7 +23,7 @@ extern "C" int emu_lsh_query_fill(void *h, const uint32_t *q, int64_t nq, const 
 extern "C" int emu_minhash_bulk(const void *tokens, int token_is_u64, const int64_t *offsets, int64_t n_docs,
                                 const uint64_t *a, const uint64_t *b, int k, int mode, int v1, const void *init,
                                 int64_t init_stride, int init_is_u64, void *out, int out_is_u64, int docs_per_unit,
-                                int grid_x);
+                                int grid_x, int gen);
 
 static uint64_t rng_state = 88172645463325252ull;
 static uint64_t rnd() {
@@ -59,7 +59,7 @@ int main() {
         for (int v1 = 0; v1 < (mode == 0 ? 2 : 1); ++v1) {
             std::vector<uint32_t> got((size_t)n_docs * k, 0);
             emu_minhash_bulk(tok.data(), 0, off.data(), n_docs, a.data(), b.data(), k, mode, v1, nullptr, 0, 0,
-                             got.data(), 0, 3, 2);
+                             got.data(), 0, 3, 2, 0);
             const bool ok = got == want;
             printf("mode %d v1 %d: %s\n", mode, v1, ok ? "identical" : "MISMATCH");
             bad += !ok;

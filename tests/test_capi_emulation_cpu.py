@@ -94,7 +94,12 @@ def test_host_pipeline_tiny_slices_long_documents_and_init(emu_lib, monkeypatch)
     out = np.zeros((len(lens), k), dtype=np.uint32)
     assert lib.dsk_minhash_bulk_host(h, tok64.ctypes.data, 1, off.ctypes.data, len(lens), None, 0, 0, out.ctypes.data, 0, 0) == 0
     assert np.array_equal(out, oc.minhash_bulk_u64tok(tok64, off, P))
-    assert lib.dsk_minhash_bulk_host(h, tok64.ctypes.data, 1, off.ctypes.data, len(lens), None, 0, 0, out.ctypes.data, 0, 1) != 0
+    # 64-bit tokens: AUTO / TWO_PHASE = the general variant of the signature kernel, EXACT = round 1's kernel; DIRECT refuses
+    for flags in (1, 3):
+        out = np.zeros((len(lens), k), dtype=np.uint32)
+        assert lib.dsk_minhash_bulk_host(h, tok64.ctypes.data, 1, off.ctypes.data, len(lens), None, 0, 0, out.ctypes.data, 0, flags) == 0
+        assert np.array_equal(out, oc.minhash_bulk_u64tok(tok64, off, P)), flags
+    assert lib.dsk_minhash_bulk_host(h, tok64.ctypes.data, 1, off.ctypes.data, len(lens), None, 0, 0, out.ctypes.data, 0, 2) != 0
     lib.dsk_perm_destroy(h)
 
 
@@ -115,7 +120,7 @@ def test_minhash_parity_tests_run_on_the_emulated_library(dsk_on_emu, golden):
     t.test_running_state_merge_and_estimators(dsk, golden)
     t.test_init_matrix_and_broadcast(dsk)
     t.test_duplicates_and_near_ties_take_slow_path(dsk)
-    t.test_unsafe_permutations_route_to_exact(dsk)
+    t.test_unsafe_permutations_take_the_general_variant(dsk)
     t.test_seeded_permutations_are_safe(dsk)
     for kernel in ("auto", "exact"):
         t.test_long_documents_are_split_and_merged(dsk, kernel)      # a 2.5M-token document cut into pieces

@@ -43,10 +43,10 @@ def emu():
                         srcs[0]], check=True)
     lib = ctypes.CDLL(so)
     vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
-    lib.emu_minhash_bulk.argtypes = [vp, ci, vp, i64, vp, vp, ci, ci, ci, vp, i64, ci, vp, ci, ci, ci]
+    lib.emu_minhash_bulk.argtypes = [vp, ci, vp, i64, vp, vp, ci, ci, ci, vp, i64, ci, vp, ci, ci, ci, ci]
     lib.emu_minhash_bulk.restype = ci
 
-    def run(tok, off, perms, mode, v1=0, init=None, out_u64=False, docs_per_unit=3, grid_x=1):
+    def run(tok, off, perms, mode, v1=0, init=None, out_u64=False, docs_per_unit=3, grid_x=1, gen=0):
         k, n = perms.shape[1], len(off) - 1
         tok = np.ascontiguousarray(tok)
         off = np.ascontiguousarray(off, dtype=np.int64)
@@ -58,7 +58,7 @@ def emu():
             ip, stride, i64f = init.ctypes.data, (0 if init.ndim == 1 else k), int(init.dtype == np.uint64)
         rc = lib.emu_minhash_bulk(tok.ctypes.data, int(tok.dtype == np.uint64), off.ctypes.data, n, a.ctypes.data,
                                   b.ctypes.data, k, mode, v1, ip, stride, i64f, out.ctypes.data, int(out_u64),
-                                  docs_per_unit, grid_x)
+                                  docs_per_unit, grid_x, gen)
         assert rc == 0
         return out
     def stats():
@@ -204,18 +204,18 @@ def test_long_documents_are_cut_into_pieces_on_the_device(emu, k):
     want = oc.minhash_bulk_u32tok(tok, off, perms)
     n = len(lens)
     vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
-    lib.emu_minhash_sig_long.argtypes = [vp, vp, i64, vp, vp, ci, vp, i64, ci, vp, ci, ci, ci, i64, ci, vp]
+    lib.emu_minhash_sig_long.argtypes = [vp, vp, i64, vp, vp, ci, vp, i64, ci, vp, ci, ci, ci, i64, ci, vp, ci]
     npieces = ctypes.c_longlong(0)
     for dpu, gx in ((3, 1), (1, 2), (32, 2)):
         out = np.zeros((n, k), dtype=np.uint32)
         assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, None, 0, 0,
-                                        out.ctypes.data, 0, dpu, gx, 100, 5, ctypes.byref(npieces)) == 0
+                                        out.ctypes.data, 0, dpu, gx, 100, 5, ctypes.byref(npieces), 0) == 0
         assert np.array_equal(out, want), (dpu, gx)
         assert npieces.value == sum(-(-int(x) // 32) for x in lens if x > 100)      # 250, 101, 1000, 481, 3000
     init = rs.randint(0, 1 << 32, size=(n, k), dtype=np.uint64)
     out64 = np.zeros((n, k), dtype=np.uint64)
     assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, init.ctypes.data, k, 1,
-                                    out64.ctypes.data, 1, 2, 2, 100, 5, None) == 0
+                                    out64.ctypes.data, 1, 2, 2, 100, 5, None, 0) == 0
     assert np.array_equal(out64, np.minimum(want.astype(np.uint64), init))
 
 
@@ -576,3 +576,154 @@ def test_randomised_differential_vs_oracle(emu):
     """A slice of the fuzz run (10 000+ cases were run when this was written: no mismatch)."""
     assert _fuzz_signature_kernel(emu, seed=20260922, iterations=120) == 120
 
+
+
+# ---- general variants of the signature kernel (GEN = 1: u32 tokens + any permutations, GEN = 2: u64 tokens) ----------
+P61 = (1 << 61) - 1
+
+
+def _unsafe_perms(k, rs):
+    """Permutations built so that small 32-bit tokens land in the 36-value set where `% (2^61-1)` takes its conditional
+    subtract (x = (j << 61) | lo with lo in [p - j, p]), mixed with seed-generated ones."""
+    perms = o.init_permutations(k, 6).copy()
+    for i in range(0, k, 3):
+        j = int(rs.randint(0, 8))
+        a = int(rs.choice([1, 3, 5, 1 << 20, (1 << 40) + 1]))
+        h = int(rs.randint(0, 200))
+        x = (j << 61) | (P61 - int(rs.randint(0, j + 1)))
+        perms[0, i] = a
+        perms[1, i] = (x - a * h) % (1 << 64)          # token h hits the subtract set for this permutation
+    return perms
+
+
+def _brute(tok, off, perms):
+    """Python big-int restatement of minhash.py:294-297 for any permutations / 64-bit tokens (small inputs only)."""
+    k = perms.shape[1]
+    out = np.full((len(off) - 1, k), 0xFFFFFFFF, dtype=np.uint64)
+    a = [int(v) for v in perms[0]]
+    b = [int(v) for v in perms[1]]
+    for d in range(len(off) - 1):
+        for t in tok[int(off[d]):int(off[d + 1])]:
+            t = int(t)
+            for j in range(k):
+                r = (((a[j] * t + b[j]) % (1 << 64)) % P61) & 0xFFFFFFFF
+                if r < out[d, j]:
+                    out[d, j] = r
+    return out.astype(np.uint32)
+
+
+@pytest.mark.parametrize("k", [16, 128, 192])
+def test_general_u32_variant_with_unsafe_permutations(emu, k):
+    rs = np.random.RandomState(100 + k)
+    perms = _unsafe_perms(k, rs)
+    lens = rs.randint(0, 60, size=24)
+    lens[:3] = [0, 1, 17]
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 200, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)     # small tokens: the subtract set is hit
+    tok[::7] = rs.randint(0, 1 << 32, size=len(tok[::7]), dtype=np.uint64).astype(np.uint32)
+    want = _brute(tok, off, perms)
+    # the inputs really exercise the conditional subtract
+    hit = 0
+    for j in range(0, k, 3):
+        for t in np.unique(tok):
+            x = (int(perms[0, j]) * int(t) + int(perms[1, j])) % (1 << 64)
+            hit += ((x & P61) + (x >> 61)) >= P61
+    assert hit > 0
+    assert np.array_equal(oc.minhash_bulk_u32tok(tok, off, perms), want)       # the C oracle agrees with the big-int form
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, gen=1), want)
+    assert np.array_equal(emu(tok, off, perms, EXACT), want)
+    # and on ordinary input the general variant equals the default one
+    tok2, off2 = _ragged(rs, 40, 300, extra_tail=2)
+    safe = o.init_permutations(k, 1)
+    assert np.array_equal(emu(tok2, off2, safe, TWO_PHASE, gen=1), oc.minhash_bulk_u32tok(tok2, off2, safe))
+
+
+@pytest.mark.parametrize("k", [64, 128, 256, 300])
+def test_u64_tokens_two_phase(emu, k):
+    """GEN = 2: 64-bit hash values (minhash.py:294 accepts anything below 2^64).  Ragged documents, the <16-byte array tail
+    (odd token count), units of several sizes, tokens that share their LOW word (phase 1 sees a tie, the exact stage must
+    tell them apart), tiny / huge values, the de-duplication table's empty marker 2^64-1 as a token."""
+    rs = np.random.RandomState(k)
+    _, off = _ragged(rs, 50, 330, extra_tail=1)
+    n = int(off[-1])
+    tok = rs.randint(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rs.randint(0, 2, size=n, dtype=np.uint64)
+    for d in range(0, len(off) - 1, 4):        # same low word, different high words
+        a, b = int(off[d]), int(off[d + 1])
+        if b - a > 8:
+            tok[a + 1:a + 5] = (tok[a] & np.uint64(0xFFFFFFFF)) | (rs.randint(0, 1 << 32, size=4, dtype=np.uint64) << np.uint64(32))
+    big = int(np.argmax(np.diff(off) >= 3))
+    tok[int(off[big]):int(off[big]) + 3] = np.array([0, 1, 0xFFFFFFFFFFFFFFFF], dtype=np.uint64)
+    perms = o.init_permutations(k, 5)
+    want = oc.minhash_bulk_u64tok(tok, off, perms)
+    for dpu, gx in ((3, 1), (32, 2), (1, 2)):
+        assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=dpu, grid_x=gx), want), (k, dpu, gx)
+    assert np.array_equal(emu(tok, off, perms, EXACT), want)
+    # running-state merge and u64 output
+    init = rs.randint(0, 1 << 32, size=want.shape, dtype=np.uint64)
+    got = emu(tok, off, perms, TWO_PHASE, init=init, out_u64=True)
+    assert got.dtype == np.uint64 and np.array_equal(got, np.minimum(want.astype(np.uint64), init))
+
+
+def test_u64_tokens_small_against_big_int_form_and_unsafe_permutations(emu):
+    rs = np.random.RandomState(3)
+    k = 32
+    perms = _unsafe_perms(k, rs)
+    lens = np.array([0, 5, 40, 16, 1, 33], dtype=np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 200, size=int(off[-1]), dtype=np.uint64)
+    tok[::3] = rs.randint(0, 1 << 63, size=len(tok[::3]), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    want = _brute(tok, off, perms)
+    assert np.array_equal(oc.minhash_bulk_u64tok(tok, off, perms), want)
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE), want)
+
+
+def test_u64_tokens_repeats_switch_deduplication_on(emu):
+    """Heavy repetition of 64-bit tokens: flagged permutations -> de-duplicating staging on the 64-bit table -> off again."""
+    rs = np.random.RandomState(5)
+    lens = [200] * 3 + [256] * 8 + [130] * 40 + [250] * 4 + [700]
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rs.randint(0, 1 << 63, size=int(off[-1]), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    for d in list(range(3, 11)) + list(range(51, 56)):
+        a, b = int(off[d]), int(off[d + 1])
+        pool = tok[a:a + max(8, (b - a) // 4)].copy()
+        pool[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        pool[1] = pool[2] ^ np.uint64(1 << 40)                 # equal low words, different tokens
+        tok[a:b] = pool[rs.randint(0, len(pool), size=b - a)]
+    perms = o.init_permutations(128, 9)
+    want = oc.minhash_bulk_u64tok(tok, off, perms)
+    emu.stats()
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=64, grid_x=1), want)
+    st = emu.stats()
+    assert st["in_place"] == 0 and st["flagged"] >= 8 and st["removed"] > 300 and st["deduped"] >= 8 and st["copied"] >= 20, st
+    assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=5, grid_x=2), want)
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_general_variants_long_documents_in_pieces(emu, gen):
+    lib = emu.lib
+    k = 128
+    rs = np.random.RandomState(40 + gen)
+    lens = np.array([30, 250, 0, 101, 100, 1000, 7, 99, 481, 40, 2100, 12], dtype=np.int64)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    if gen == 2:
+        tok = rs.randint(0, 1 << 63, size=int(off[-1]), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+        perms = o.init_permutations(k, 4)
+        want = oc.minhash_bulk_u64tok(tok, off, perms)
+    else:
+        tok = rs.randint(0, 1 << 32, size=int(off[-1]), dtype=np.uint64).astype(np.uint32)
+        perms = _unsafe_perms(k, rs)
+        tok[::5] = rs.randint(0, 200, size=len(tok[::5]))
+        want = oc.minhash_bulk_u32tok(tok, off, perms)
+    a, b = np.ascontiguousarray(perms[0]), np.ascontiguousarray(perms[1])
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.emu_minhash_sig_long.argtypes = [vp, vp, i64, vp, vp, ci, vp, i64, ci, vp, ci, ci, ci, i64, ci, vp, ci]
+    n = len(lens)
+    for dpu, gx in ((3, 1), (32, 2)):
+        out = np.zeros((n, k), dtype=np.uint32)
+        assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, None, 0, 0,
+                                        out.ctypes.data, 0, dpu, gx, 100, 5, None, gen) == 0
+        assert np.array_equal(out, want), (gen, dpu, gx)

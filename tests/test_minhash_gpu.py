@@ -62,10 +62,11 @@ def test_long_and_small_docs(dsk, golden, kernel):
 def test_u64_tokens_golden(dsk, golden):
     g = golden("minhash")
     P = o.init_permutations(64, 3)
-    sig = dsk.engine.bulk_signatures(g["u64_tokens"], g["u64_offsets"], P, out_u64=True)
-    assert np.array_equal(sig, g["u64_sig"])
-    with pytest.raises(ValueError):  # fast kernels are not exact for 64-bit hashes
-        dsk.engine.bulk_signatures(g["u64_tokens"], g["u64_offsets"], P, kernel="two_phase")
+    for kernel in ("auto", "two_phase", "exact"):   # auto / two_phase: the general variant of the signature kernel
+        sig = dsk.engine.bulk_signatures(g["u64_tokens"], g["u64_offsets"], P, out_u64=True, kernel=kernel)
+        assert np.array_equal(sig, g["u64_sig"]), kernel
+    with pytest.raises(ValueError):  # r = lo32(x) + top3(x) everywhere is not exact for 64-bit hashes
+        dsk.engine.bulk_signatures(g["u64_tokens"], g["u64_offsets"], P, kernel="direct")
 
 
 def test_sha1_update_batch_like_reference_gpu_test(dsk, golden):
@@ -167,14 +168,15 @@ def test_duplicates_and_near_ties_take_slow_path(dsk):
     tok = np.concatenate(docs)
     want = oc.minhash_bulk_u32tok(tok, off, P)
     h = nv.perm_handle(P)
-    kernels = ["auto", "exact"] + (["two_phase", "direct"] if h.n_unsafe == 0 else [])
+    kernels = ["auto", "exact", "two_phase"] + (["direct"] if h.n_unsafe == 0 else [])
     for kernel in kernels:
         assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel=kernel), want), kernel
 
 
-def test_unsafe_permutations_route_to_exact(dsk):
-    # x = a*h + b can hit the 36 values where `% (2^61-1)` subtracts: the fast formula would be
-    # off by one there, so the handle must flag it and AUTO must stay bit-exact.
+def test_unsafe_permutations_take_the_general_variant(dsk):
+    # x = a*h + b can hit the 36 values where `% (2^61-1)` subtracts: r = lo32(x) + top3(x) would be off by one there, so
+    # the handle must flag it; AUTO / TWO_PHASE then run the signature kernel's general variant (conditional subtract in
+    # its exact stage, window 8) and stay bit-exact, DIRECT refuses.
     from datasketch_b200 import _native as nv
     p = (1 << 61) - 1
     a = np.array([1, 1, 3, 0, 1 << 40, 5], dtype=np.uint64)
@@ -187,8 +189,9 @@ def test_unsafe_permutations_route_to_exact(dsk):
     want = o.bulk_signatures_csr(tok, off, 6, 0, permutations=P).astype(np.uint32)
     assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P), want)
     assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel="exact"), want)
+    assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel="two_phase"), want)
     with pytest.raises(ValueError):
-        dsk.engine.bulk_signatures(tok, off, P, kernel="two_phase")
+        dsk.engine.bulk_signatures(tok, off, P, kernel="direct")
     # the values the fast formula would get wrong are really exercised:
     hits = [(int(ai) * int(t) + int(bi)) % (1 << 64) for ai, bi in zip(a, b) for t in tok]
     assert any(((x & p) + (x >> 61)) >= p for x in hits)

@@ -96,3 +96,100 @@ def test_repeated_calls_reuse_counters_and_workspace():
     torch.cuda.synchronize()
     for i in (0, 1, 63, 64, 65, 128, 149):
         assert np.array_equal(outs[i].cpu().numpy().view(np.uint32), want), i
+
+
+# ---- general variants: 64-bit tokens (GEN = 2) and permutations that reach the conditional subtract (GEN = 1) ---------
+P61 = (1 << 61) - 1
+
+
+def _unsafe_perms(k, rs):
+    """Every third permutation is built so that one small token lands in the set where `% (2^61-1)` subtracts."""
+    perms = o.init_permutations(k, 6).copy()
+    for i in range(0, k, 3):
+        j = int(rs.randint(0, 8))
+        a = int(rs.choice([1, 3, 5, 1 << 20, (1 << 40) + 1]))
+        h = int(rs.randint(0, 200))
+        x = (j << 61) | (P61 - int(rs.randint(0, j + 1)))
+        perms[0, i] = a
+        perms[1, i] = (x - a * h) % (1 << 64)
+    return perms
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_u64_tokens_randomised_shapes_against_the_oracle(seed):
+    """The same sweep with 64-bit hash values (minhash.py:294 accepts anything below 2^64) through both entries."""
+    import torch
+    import datasketch_b200 as dsk
+    rs = np.random.RandomState(3000 + seed)
+    for it in range(6):
+        style = int(rs.randint(0, 5))
+        tok32, off = _case(rs, style)
+        T = len(tok32)
+        hi = rs.randint(0, 1 << 32, size=T, dtype=np.uint64)
+        if it % 3 == 0:
+            hi[:] = hi % np.uint64(3)          # few distinct high words: equal low words often are equal tokens
+        tok = (hi << np.uint64(32)) | tok32.astype(np.uint64)
+        k = int(rs.choice([64, 100, 128, 128, 256, 300]))
+        P = o.init_permutations(k, int(rs.randint(1, 40)))
+        want = oc.minhash_bulk_u64tok(tok, off, P)
+        d_tok = torch.from_numpy(np.concatenate([tok, np.zeros(2, np.uint64)]).view(np.int64)).cuda()[:T]
+        d_off = torch.from_numpy(off).cuda()
+        got = dsk.engine.bulk_signatures_device(d_tok, d_off, T, P).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), dict(seed=seed, it=it, style=style, k=k, docs=len(off) - 1, tokens=T)
+        if it < 2:
+            assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P), want)
+            assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel="exact"), want)
+
+
+def test_unsafe_permutations_randomised_against_the_oracle():
+    import torch
+    import datasketch_b200 as dsk
+    from datasketch_b200 import _native as nv
+    rs = np.random.RandomState(77)
+    for it in range(6):
+        tok, off = _case(rs, int(rs.randint(0, 5)))
+        tok[::3] = rs.randint(0, 200, size=len(tok[::3]))      # small tokens hit the subtract set of the built permutations
+        k = int(rs.choice([33, 128, 256]))
+        P = _unsafe_perms(k, rs)
+        assert nv.perm_handle(P).n_unsafe > 0
+        want = oc.minhash_bulk_u32tok(tok, off, P)
+        d_tok = torch.from_numpy(np.concatenate([tok, np.zeros(4, np.uint32)]).view(np.int32)).cuda()[:len(tok)]
+        d_off = torch.from_numpy(off).cuda()
+        got = dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), it
+        assert np.array_equal(dsk.engine.bulk_signatures(tok, off, P, kernel="two_phase"), want)
+    # the general variant on ordinary input equals the default one (same documents, a handle that is flagged unsafe)
+    tok, off = _case(rs, 2)
+    P = o.init_permutations(128, 1)
+    Pu = P.copy()
+    Pu[0, 5], Pu[1, 5] = 1, P61 - 3                         # token 3 -> x = p: the subtract fires
+    assert nv.perm_handle(Pu).n_unsafe == 1
+    got = dsk.engine.bulk_signatures(tok, off, Pu)
+    ref = dsk.engine.bulk_signatures(tok, off, P)
+    keep = np.arange(128) != 5
+    assert np.array_equal(got[:, keep], ref[:, keep]) and np.array_equal(got, oc.minhash_bulk_u32tok(tok, off, Pu))
+
+
+def test_u64_tokens_full_size_properties():
+    """250k documents x 256 64-bit tokens: sampled rows against the C oracle, plus size-independent properties --
+    reversing every document, and appending a copy of each document's first half, leave the matrix unchanged."""
+    import torch
+    import datasketch_b200 as dsk
+    rs = np.random.RandomState(9)
+    n, t = 250_000, 256
+    tok = rs.randint(0, 1 << 63, size=n * t, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    off = np.arange(n + 1, dtype=np.int64) * t
+    P = o.init_permutations(128, 1)
+    d_tok = torch.from_numpy(tok.view(np.int64)).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    sig = dsk.engine.bulk_signatures_device(d_tok, d_off, tok.size, P)
+    idx = np.arange(0, n, 997)
+    sub = tok.reshape(n, t)[idx].reshape(-1)
+    sub_off = np.arange(len(idx) + 1, dtype=np.int64) * t
+    got = sig.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[idx], oc.minhash_bulk_u64tok(sub, sub_off, P))
+    d_rev = torch.flip(d_tok.view(n, t), dims=[1]).contiguous().view(-1)
+    assert torch.equal(dsk.engine.bulk_signatures_device(d_rev, d_off, tok.size, P), sig)
+    d_dup = torch.cat([d_tok.view(n, t), d_tok.view(n, t)[:, : t // 2]], dim=1).contiguous().view(-1)
+    d_off2 = torch.from_numpy(np.arange(n + 1, dtype=np.int64) * (t + t // 2)).cuda()
+    assert torch.equal(dsk.engine.bulk_signatures_device(d_dup, d_off2, d_dup.numel(), P), sig)

@@ -22,7 +22,7 @@ g = torch.Generator(device="cuda").manual_seed(1)
 only = set(sys.argv[1:])
 
 
-def run(name, lens, k, repeat_share=0.0, iters=5):
+def run(name, lens, k, repeat_share=0.0, iters=5, u64=False, unsafe=False, kernel="auto"):
     if only and name not in only:
         return
     lens = torch.as_tensor(lens, dtype=torch.int64, device=dev)
@@ -38,27 +38,33 @@ def run(name, lens, k, repeat_share=0.0, iters=5):
         src = off[doc] + (torch.rand(nt, device=dev, generator=g) * pos).long()
         tok = torch.where(rep, tok[src], tok)
     perms = _make_permutations(k, 1)
+    if unsafe:      # one user-supplied permutation that reaches the conditional subtract of `% (2^61-1)` (token 3 -> x = p):
+        perms = perms.copy()    # the handle is flagged and the kernel's general u32 variant (GEN = 1) runs
+        perms[0, 5], perms[1, 5] = 1, (1 << 61) - 1 - 3
+    if u64:         # 64-bit hash values: a random high word on every token (GEN = 2)
+        hi = torch.randint(0, 1 << 32, (nt,), dtype=torch.int64, device=dev, generator=g)
+        tok = hi.mul_(1 << 32).add_(tok.to(torch.int64) & 0xFFFFFFFF)
     sig = torch.empty((n, k), dtype=torch.int32, device=dev)
     for _ in range(3):
-        dsk.engine.bulk_signatures_device(tok, off, nt, perms, d_out=sig)
+        dsk.engine.bulk_signatures_device(tok, off, nt, perms, d_out=sig, kernel=kernel)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        dsk.engine.bulk_signatures_device(tok, off, nt, perms, d_out=sig)
+        dsk.engine.bulk_signatures_device(tok, off, nt, perms, d_out=sig, kernel=kernel)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     idx = np.unique(np.linspace(0, n - 1, 150).astype(np.int64))
     h_off = off.cpu().numpy()
-    h_tok = tok.cpu().numpy().view(np.uint32)
+    h_tok = tok.cpu().numpy().view(np.uint64 if u64 else np.uint32)
     sub_off = np.zeros(len(idx) + 1, dtype=np.int64)
     np.cumsum(h_off[idx + 1] - h_off[idx], out=sub_off[1:])
-    sub = np.concatenate([h_tok[h_off[i]:h_off[i + 1]] for i in idx]) if len(idx) else np.zeros(0, np.uint32)
-    want = oc.minhash_bulk_u32tok(np.ascontiguousarray(sub), sub_off, perms)
+    sub = np.concatenate([h_tok[h_off[i]:h_off[i + 1]] for i in idx]) if len(idx) else np.zeros(0, h_tok.dtype)
+    want = (oc.minhash_bulk_u64tok if u64 else oc.minhash_bulk_u32tok)(np.ascontiguousarray(sub), sub_off, perms)
     got = sig[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.uint32)
     evals = float(nt) * k
-    print(json.dumps({"shape": name, "docs": n, "tokens": nt, "num_perm": k, "repeat_share": repeat_share, "ms": round(ms, 4),
+    print(json.dumps({"shape": name, "tokens_are": "u64" if u64 else "u32", "kernel": kernel, "docs": n, "tokens": nt, "num_perm": k, "repeat_share": repeat_share, "ms": round(ms, 4),
                       "signatures_per_s": n / ms * 1e3, "evaluations_per_s": evals / ms * 1e3,
                       "frac_of_imad_floor": evals / ms * 1e3 / (148 * 64 * 1.965e9),
                       "rows_identical": bool(np.array_equal(got, want))}), flush=True)
@@ -79,3 +85,11 @@ run("k64_2Mx256", np.full(2_000_000, 256), 64)
 for share in (0.01, 0.1, 0.5):
     run("repeats_500kx256", np.full(500_000, 256), 128, repeat_share=share)
 run("repeats_ragged_500k", rs.randint(128, 385, size=500_000), 128, repeat_share=0.1)
+# general variants of the signature kernel next to round 1's EXACT kernel (what these inputs were routed to before)
+run("u64_tokens_1Mx256", np.full(1_000_000, 256), 128, u64=True)
+run("u64_tokens_1Mx256_exact_kernel", np.full(1_000_000, 256), 128, u64=True, kernel="exact", iters=3)
+run("u64_tokens_ragged_1M_128to384", rs.randint(128, 385, size=1_000_000), 128, u64=True)
+run("u64_tokens_repeats_500kx256", np.full(500_000, 256), 128, repeat_share=0.1, u64=True)
+run("u64_tokens_long_20k_x12800", np.full(20_000, 12_800), 128, u64=True)
+run("unsafe_permutation_1Mx256", np.full(1_000_000, 256), 128, unsafe=True)
+run("unsafe_permutation_1Mx256_exact_kernel", np.full(1_000_000, 256), 128, unsafe=True, kernel="exact", iters=3)
