@@ -31,12 +31,6 @@ def run(name, lens, k, repeat_share=0.0, iters=5, u64=False, unsafe=False, kerne
     off[1:] = torch.cumsum(lens, 0)
     nt = int(off[-1].item())
     tok = torch.randint(-2 ** 31, 2 ** 31 - 1, (nt + 4,), dtype=torch.int32, device=dev, generator=g)[:nt]
-    if repeat_share > 0:   # position i of a document repeats a token from an earlier position of the same document
-        doc = torch.repeat_interleave(torch.arange(n, device=dev), lens)
-        pos = torch.arange(nt, device=dev) - off[doc]
-        rep = (torch.rand(nt, device=dev, generator=g) < repeat_share) & (pos > 0)
-        src = off[doc] + (torch.rand(nt, device=dev, generator=g) * pos).long()
-        tok = torch.where(rep, tok[src], tok)
     perms = _make_permutations(k, 1)
     if unsafe:      # one user-supplied permutation that reaches the conditional subtract of `% (2^61-1)` (token 3 -> x = p):
         perms = perms.copy()    # the handle is flagged and the kernel's general u32 variant (GEN = 1) runs
@@ -44,6 +38,12 @@ def run(name, lens, k, repeat_share=0.0, iters=5, u64=False, unsafe=False, kerne
     if u64:         # 64-bit hash values: a random high word on every token (GEN = 2)
         hi = torch.randint(0, 1 << 32, (nt,), dtype=torch.int64, device=dev, generator=g)
         tok = hi.mul_(1 << 32).add_(tok.to(torch.int64) & 0xFFFFFFFF)
+    if repeat_share > 0:   # position i of a document repeats a token from an earlier position of the same document
+        doc = torch.repeat_interleave(torch.arange(n, device=dev), lens)
+        pos = torch.arange(nt, device=dev) - off[doc]
+        rep = (torch.rand(nt, device=dev, generator=g) < repeat_share) & (pos > 0)
+        src = off[doc] + (torch.rand(nt, device=dev, generator=g) * pos).long()
+        tok = torch.where(rep, tok[src], tok)
     sig = torch.empty((n, k), dtype=torch.int32, device=dev)
     for _ in range(3):
         dsk.engine.bulk_signatures_device(tok, off, nt, perms, d_out=sig, kernel=kernel)
