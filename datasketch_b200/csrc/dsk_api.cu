@@ -139,6 +139,17 @@ struct CounterLease {
     }
 };
 
+// Entry points that take a handle launch on the HANDLE's device: the caller's current device is switched for the call and
+// restored (one process may drive several devices).
+struct DevGuard {
+    int prev = 0;
+    bool switched = false;
+    explicit DevGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 struct dsk_wmh {
     int device = 0, ss = 0, ss_pad = 0, dim = 0;
     float *d_par = nullptr;  // rs_t | lncs_t | betas_t, each [dim][ss_pad]
@@ -354,6 +365,7 @@ int dsk_minhash_bulk_ws(const dsk_perm *perm, const void *d_tokens, int token_is
         prm.piece_hdr = static_cast<unsigned *>(d_workspace);
         prm.pieces = reinterpret_cast<PieceDesc *>(static_cast<char *>(d_workspace) + kPieceHdrBytes);
     }
+    DevGuard guard(perm->device);
     CounterLease lease(perm, (cudaStream_t)stream);
     prm.work_counter = lease.ptr;
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
@@ -406,6 +418,7 @@ int dsk_minhash_bulk_gather(const dsk_perm *perm, const void *d_tokens, int toke
             set_error("dsk_minhash_bulk_gather: peer pointer %d is null or not 16-byte aligned", i);
             return DSK_ERR_ALIGN;
         }
+    DevGuard guard(perm->device);
     CounterLease lease(perm, (cudaStream_t)stream);
     prm.work_counter = lease.ptr;
     DSK_CUDA(launch_minhash_bulk(prm, mode, token_is_u64, dev->sm_count, (cudaStream_t)stream));
@@ -625,6 +638,7 @@ int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64_t *d_ou
     int rc = get_dev(g->device, &dev);
     if (rc) return rc;
     const size_t plane = (size_t)g->dim * g->ss_pad;
+    DevGuard guard(g->device);
     DSK_CUDA(launch_wmh(g->d_par, g->d_par + plane, g->d_par + 2 * plane, g->ss, g->ss_pad, g->dim, d_v, n, d_out,
                         d_status, (flags & DSK_WMH_MINHASH_MANY) != 0, (flags & DSK_WMH_INPUT_LOG) != 0, dev->sm_count,
                         (cudaStream_t)stream));
@@ -701,6 +715,7 @@ int dsk_lsh_insert(dsk_lsh *ix, const uint32_t *d_sig, int64_t n, void *stream) 
     DevInfo *dev;
     int rc = get_dev(ix->device, &dev);
     if (rc) return rc;
+    DevGuard guard(ix->device);
     DSK_CUDA(launch_lsh_insert(ix->dev, d_sig, ix->n_docs, n, dev->sm_count, (cudaStream_t)stream));
     ix->n_docs += n;
     return DSK_OK;
@@ -714,6 +729,7 @@ int dsk_lsh_query_count(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, i
     DevInfo *dev;
     int rc = get_dev(ix->device, &dev);
     if (rc) return rc;
+    DevGuard guard(ix->device);
     DSK_CUDA(launch_lsh_query(ix->dev, d_qsig, nq, ix->n_docs, d_counts, nullptr, nullptr, 0, dev->sm_count,
                               (cudaStream_t)stream));
     return DSK_OK;
@@ -728,6 +744,7 @@ int dsk_lsh_query_fill(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, co
     DevInfo *dev;
     int rc = get_dev(ix->device, &dev);
     if (rc) return rc;
+    DevGuard guard(ix->device);
     DSK_CUDA(launch_lsh_query(ix->dev, d_qsig, nq, ix->n_docs, nullptr, d_ptr, d_idx, 1, dev->sm_count,
                               (cudaStream_t)stream));
     return DSK_OK;

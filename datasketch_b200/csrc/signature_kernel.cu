@@ -131,7 +131,17 @@ void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int6
 #ifndef DSK_SIG_APPEND_NOINLINE
 #define DSK_SIG_APPEND_NOINLINE 1   // the long-document piece append as an out-of-line call
 #endif
-template <int P> constexpr bool kPend = DSK_SIG_PEND && P <= 4;
+// K > 128 (8 permutations per lane): CTAs per SM, software pipelining of the block loop, folded tracking ops
+#ifndef DSK_SIG_OCC8
+#define DSK_SIG_OCC8 3
+#endif
+#ifndef DSK_SIG_SWP8
+#define DSK_SIG_SWP8 1
+#endif
+#ifndef DSK_SIG_PEND8
+#define DSK_SIG_PEND8 1
+#endif
+template <int P> constexpr bool kPend = DSK_SIG_PEND && (P <= 4 || DSK_SIG_PEND8);
 
 template <int P, int OCC, bool PIECES, int GEN>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
@@ -383,7 +393,7 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                     const uint32_t *q = src;
                     const uint32_t *const qe = src + nblk * 16;
                     uint32_t lb = 0;
-                    if constexpr (P > 4) {
+                    if constexpr (P > 4 && !DSK_SIG_SWP8) {
 #pragma unroll 1
                         for (; q < qe; q += 16, ++lb) {
                             uint32_t t[16];
@@ -638,7 +648,7 @@ static cudaError_t launch_sig_k(const BulkParams &prm, int sm_count, cudaStream_
     // K > 128: 8 permutations per lane, or (DSK_SIG_WIDE=4, an A/B switch) K-slices of 128 on blockIdx.y with 4 per lane
     static const bool wide4 = [] { const char *e = getenv("DSK_SIG_WIDE"); return e && atoi(e) == 4; }();
     if (wide4) return launch_sig<4, 4, GEN>(prm, sm_count, s);
-    return launch_sig<8, 4, GEN>(prm, sm_count, s);
+    return launch_sig<8, DSK_SIG_OCC8, GEN>(prm, sm_count, s);
 }
 
 // 4 CTAs (16 warps) per SM: 5 and 6 were measured slower (register cap, profiles/r2i_kernel_variants_ab.txt)

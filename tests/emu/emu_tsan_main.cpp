@@ -64,6 +64,29 @@ int main() {
             printf("mode %d v1 %d: %s\n", mode, v1, ok ? "identical" : "MISMATCH");
             bad += !ok;
         }
+    {   // general variants: u32 tokens with GEN = 1, and 64-bit tokens (GEN = 2: word ring, two staged planes, 64-bit
+        // de-duplication table) -- repeats kept (equal u32 tokens -> equal u64 tokens), so the flagged path and the
+        // de-duplicating stage run under the race detector too
+        std::vector<uint32_t> got((size_t)n_docs * k, 0);
+        emu_minhash_bulk(tok.data(), 0, off.data(), n_docs, a.data(), b.data(), k, 0, 0, nullptr, 0, 0, got.data(), 0, 3, 2, 1);
+        bool ok = got == want;
+        printf("general u32 variant: %s\n", ok ? "identical" : "MISMATCH");
+        bad += !ok;
+        std::vector<uint64_t> tok64(tok.size());
+        for (size_t i = 0; i < tok.size(); ++i) tok64[i] = ((uint64_t)(tok[i] * 2654435761u) << 32) | tok[i];
+        std::vector<uint32_t> want64((size_t)n_docs * k, 0xFFFFFFFFu);
+        for (int d = 0; d < n_docs; ++d)
+            for (int64_t i = off[d]; i < off[d + 1]; ++i)
+                for (int j = 0; j < k; ++j) {
+                    const uint64_t x = a[j] * tok64[i] + b[j];
+                    const uint32_t r = (uint32_t)(x % p61);
+                    if (r < want64[(size_t)d * k + j]) want64[(size_t)d * k + j] = r;
+                }
+        emu_minhash_bulk(tok64.data(), 1, off.data(), n_docs, a.data(), b.data(), k, 0, 0, nullptr, 0, 0, got.data(), 0, 3, 2, 0);
+        ok = got == want64;
+        printf("u64 tokens: %s\n", ok ? "identical" : "MISMATCH");
+        bad += !ok;
+    }
     {   // LeanMinHash codec: 4-stage bulk-copy tile pipeline, several tiles per CTA, ragged last tile
         const int lk = 128;
         const int64_t ln = 777;

@@ -257,7 +257,7 @@ def test_thread_sanitizer_finds_no_race_in_the_ring_protocol():
     if run.returncode not in (0, 1, 66) or "unexpected memory mapping" in text:
         pytest.skip("ThreadSanitizer cannot run in this container: " + text[-200:])
     assert "data race" not in text and run.returncode == 0, text[-2000:]
-    assert text.count("identical") == 6
+    assert text.count("identical") == 8
 
 
 # ---- codec kernels (codec_kernels.cu): TMA tile pipeline and the simple kernels ----------------------------------

@@ -82,6 +82,7 @@ run("same_tokens_as_1000_docs", np.full(1000, 2500), 128, iters=10)
 run("reference_bench_shape_1x50k", np.array([50_000]), 128, iters=20)
 run("k256_2Mx128", np.full(2_000_000, 128), 256)
 run("k64_2Mx256", np.full(2_000_000, 256), 64)
+run("k192_2Mx128", np.full(2_000_000, 128), 192)
 for share in (0.01, 0.1, 0.5):
     run("repeats_500kx256", np.full(500_000, 256), 128, repeat_share=share)
 run("repeats_ragged_500k", rs.randint(128, 385, size=500_000), 128, repeat_share=0.1)
