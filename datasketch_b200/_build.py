@@ -58,6 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libdsk_b200.so must be built where the CUDA toolkit is installed")
+    stamp = source_hash()   # of what nvcc is about to read: an edit made while it runs must leave the library stale
     cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
@@ -67,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write(proc.stdout + proc.stderr)
     with open(STAMP, "w") as f:
-        f.write(source_hash())
+        f.write(stamp)
     return LIB
 
 

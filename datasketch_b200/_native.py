@@ -54,6 +54,7 @@ SIGNATURES = {
     "dsk_lsh_destroy": (None, [c_void_p]),
     "dsk_lsh_size": (c_int, [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
     "dsk_lsh_insert": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dsk_lsh_insert_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p]),
     "dsk_lsh_query_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dsk_lsh_query_fill": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dsk_exclusive_scan": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -721,6 +721,67 @@ int dsk_lsh_insert(dsk_lsh *ix, const uint32_t *d_sig, int64_t n, void *stream) 
     return DSK_OK;
 }
 
+int dsk_lsh_insert_tokens(dsk_lsh *ix, const dsk_perm *perm, const void *d_tokens, int token_is_u64,
+                          const int64_t *d_offsets, int64_t n_docs, int64_t n_tokens, void *stream) {
+    if (!ix || !perm || !d_offsets || n_docs < 0 || n_tokens < 0 || (n_tokens > 0 && !d_tokens)) {
+        set_error("dsk_lsh_insert_tokens: bad arguments");
+        return DSK_ERR_INVALID;
+    }
+    if (perm->num_perm != ix->dev.k || perm->device != ix->device) {
+        set_error("dsk_lsh_insert_tokens: the permutation handle has num_perm=%d on device %d, the index num_perm=%d on device %d",
+                  perm->num_perm, perm->device, ix->dev.k, ix->device);
+        return DSK_ERR_INVALID;
+    }
+    if (ix->n_docs + n_docs > ix->dev.cap_docs) {
+        set_error("dsk_lsh_insert_tokens: capacity exceeded (%lld + %lld > %lld)", (long long)ix->n_docs, (long long)n_docs,
+                  (long long)ix->dev.cap_docs);
+        return DSK_ERR_INVALID;
+    }
+    if (n_docs == 0) return DSK_OK;
+    if (((uintptr_t)d_tokens & 15) != 0 || ((uintptr_t)d_offsets & 7) != 0) {
+        set_error("dsk_lsh_insert_tokens: d_tokens must be 16-byte aligned and d_offsets 8-byte aligned");
+        return DSK_ERR_ALIGN;
+    }
+    DevInfo *dev;
+    int rc = get_dev(ix->device, &dev);
+    if (rc) return rc;
+    uint32_t *rows = ix->dev.sig + ix->n_docs * ix->dev.k;   // the new documents' rows in the index's own storage
+    BulkParams prm{};
+    prm.tokens = d_tokens;
+    prm.offsets = d_offsets;
+    prm.n_docs = n_docs;
+    prm.n_tokens = n_tokens;
+    prm.a_lo = perm->d_tab;
+    prm.a_hi = perm->d_tab + perm->kpad;
+    prm.b_lo = perm->d_tab + 2 * perm->kpad;
+    prm.b_hi = perm->d_tab + 3 * perm->kpad;
+    prm.b_lo7 = perm->d_tab + 4 * perm->kpad;
+    prm.b_lo8 = perm->d_tab + 5 * perm->kpad;
+    prm.gen = token_is_u64 ? 2 : (perm->n_unsafe ? 1 : 0);
+    prm.k = perm->num_perm;
+    prm.out = rows;
+    prm.out_is_u64 = 0;
+    const bool fused = prm.gen == 0 && prm.k <= 256 && (((uintptr_t)rows & 15) == 0);
+    DevGuard guard(ix->device);
+    {
+        CounterLease lease(perm, (cudaStream_t)stream);
+        prm.work_counter = lease.ptr;
+        if (fused) {
+            prm.lsh_slots = ix->dev.slots;
+            prm.lsh_next = ix->dev.next;
+            prm.lsh_cap_slots = ix->dev.cap_slots;
+            prm.lsh_doc0 = ix->n_docs;
+            prm.lsh_b = ix->dev.b;
+            prm.lsh_r = ix->dev.r;
+        }
+        DSK_CUDA(launch_minhash_bulk(prm, MODE_TWO_PHASE, token_is_u64, dev->sm_count, (cudaStream_t)stream));
+    }
+    if (!fused)   // rows are in place already: the insert kernel's copy of them is a self-copy
+        DSK_CUDA(launch_lsh_insert(ix->dev, rows, ix->n_docs, n_docs, dev->sm_count, (cudaStream_t)stream));
+    ix->n_docs += n_docs;
+    return DSK_OK;
+}
+
 int dsk_lsh_query_count(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, int64_t *d_counts, void *stream) {
     if (!ix || nq < 0 || (nq > 0 && (!d_qsig || !d_counts))) {
         set_error("dsk_lsh_query_count: bad arguments");

@@ -66,6 +66,13 @@ struct BulkParams {
     // general variants of the signature kernel (appended last: the layout the default variant sees stays as it was)
     const uint32_t *b_lo8;      // b_lo + 8: the addend of L' when `% p` may take its conditional subtract (window 8)
     int gen;                    // 0 = u32 tokens + safe permutations, 1 = u32 tokens + any permutations, 2 = u64 tokens
+    // fused LSH insert (signature_kernel.cu, template LSH): when lsh_slots != nullptr the warp that finishes document d also
+    // inserts it into the device-resident LSH index as document lsh_doc0 + d (the bucket tables' DRAM latency hides behind the
+    // other warps' integer work); `out` then is the index's own signature storage (u32, row lsh_doc0 + d at out + d * k)
+    uint64_t *lsh_slots;        // LshDev::slots
+    int32_t *lsh_next;          // LshDev::next
+    int64_t lsh_cap_slots, lsh_doc0;
+    int lsh_b, lsh_r;
 };
 struct PieceDesc { int64_t row, start, end, reserved; };
 constexpr int kPieceHdrBytes = 512;
@@ -211,5 +218,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 #endif  // !DSK_EMU
+
+// ---- LSH bucket fingerprints (lsh_kernels.cu; the signature kernel's fused insert epilogue) ------------------------------
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ uint64_t lsh_mix64(uint64_t h) {
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    return h;
+}
+
+__device__ __forceinline__ uint64_t band_fp(const uint32_t *v, int r, int band) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)band;
+    for (int q = 0; q < r; ++q) h = (h ^ v[q]) * 0xFF51AFD7ED558CCDull + 0x2545F4914F6CDD1Dull;
+    h = lsh_mix64(h);
+    return h == kEmptyKey ? h - 1 : h;
+}
 
 }  // namespace dsk

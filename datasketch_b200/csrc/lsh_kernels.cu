@@ -15,19 +15,7 @@
 
 namespace dsk {
 
-constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
-
-__device__ __forceinline__ uint64_t lsh_mix64(uint64_t h) {
-    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
-    return h;
-}
-
-__device__ __forceinline__ uint64_t band_fp(const uint32_t *v, int r, int band) {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)band;
-    for (int q = 0; q < r; ++q) h = (h ^ v[q]) * 0xFF51AFD7ED558CCDull + 0x2545F4914F6CDD1Dull;
-    h = lsh_mix64(h);
-    return h == kEmptyKey ? h - 1 : h;
-}
+// kEmptyKey, lsh_mix64, band_fp: dsk_common.cuh (shared with the signature kernel's fused insert epilogue)
 
 __device__ __forceinline__ bool tuple_eq(const uint32_t *a, const uint32_t *b, int r) {
     bool eq = true;
@@ -55,7 +43,7 @@ __global__ void __launch_bounds__(256) lsh_insert_kernel(const LshDev ix, const 
         for (int e = threadIdx.x; e < nd * ix.k; e += blockDim.x) {
             const uint32_t v = __ldg(src + e);
             s_rows[e] = v;
-            keep[e] = v;
+            if (keep != src) keep[e] = v;   // (dsk_lsh_insert_tokens' two-kernel route built the rows in place)
         }
         __syncthreads();
         for (int pair = threadIdx.x; pair < nd * ix.b; pair += blockDim.x) {

@@ -30,6 +30,10 @@
 //            unchanged (one IMAD on the LOW words) and only the exact stage evaluates the 64-bit form.  GEN = 1: u32 tokens
 //            with permutations that can reach the subtract (user-supplied ones); GEN = 2: u64 tokens (hash values up to
 //            2^64-1, minhash.py:294) -- staged as a low-word plane (phase 1) and a high-word plane (exact stage only).
+//   lsh      (template LSH) fused MinHashLSH insert: the warp that finishes a document puts the row into its line buffer,
+//            lane j fingerprints band j and does the bucket update (atomicCAS claim + atomicExch chain head + link store,
+//            as lsh_insert_kernel) -- the tables' DRAM latency hides behind the other warps' integer work, and the
+//            signature matrix is never read back.  Replaces lsh.py:326-347 for a whole batch of token lists.
 //   flagged  a permutation with another block inside the window (m2 - m <= 69), a second group inside the window,
 //            or a minimum so small that L'-7 could wrap (m < 32) is resolved by the whole warp, two permutations
 //            at a time: every lane filters 1/32 of the sub-piece's tokens with L' and evaluates r exactly for the
@@ -143,8 +147,9 @@ void append_pieces(unsigned *piece_hdr, PieceDesc *pieces, int piece_shift, int6
 #endif
 template <int P> constexpr bool kPend = DSK_SIG_PEND && (P <= 4 || DSK_SIG_PEND8);
 
-template <int P, int OCC, bool PIECES, int GEN>
+template <int P, int OCC, bool PIECES, int GEN, bool LSH = false>
 __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const BulkParams prm) {
+    static_assert(!(LSH && PIECES), "the fused insert needs whole rows: no piece mode");
     constexpr int TW = GEN == 2 ? 2 : 1;            // 32-bit words per token; the ring and its copies count WORDS
     constexpr int SUB = GEN == 2 ? kHiOff : kSubTok;  // tokens per sub-piece
     constexpr uint32_t W = kWin<GEN>;
@@ -591,6 +596,30 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                     }
                 }
             }
+            // ---- fused LSH insert: row -> line buffer, lane <-> band (lsh_insert_kernel's update, one document) ----------
+            if constexpr (LSH) {
+                __syncwarp();   // every lane is done with the staged tokens of this document's last sub-piece
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    if (kl + j < K) buf[kl + j] = acc[j];
+                __syncwarp();
+                const uint64_t mask = (uint64_t)prm.lsh_cap_slots - 1;
+                const int64_t doc = prm.lsh_doc0 + d;
+                for (int band = lane; band < prm.lsh_b; band += 32) {
+                    const uint64_t fp = band_fp(buf + band * prm.lsh_r, prm.lsh_r, band);
+                    uint64_t *tabp = prm.lsh_slots + (int64_t)band * prm.lsh_cap_slots * 2;
+                    uint64_t slot = lsh_mix64(fp) & mask;
+                    while (true) {
+                        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(tabp + 2 * slot),
+                                                                  (unsigned long long)kEmptyKey, (unsigned long long)fp);
+                        if (prev == kEmptyKey || prev == fp) break;
+                        slot = (slot + 1) & mask;
+                    }
+                    const int32_t old = atomicExch(reinterpret_cast<int32_t *>(tabp + 2 * slot + 1), (int32_t)doc);
+                    prm.lsh_next[doc * prm.lsh_b + band] = old;
+                }
+                __syncwarp();   // the next document stages into the line buffer
+            }
             start = end;
         }
         drain(c_next);   // (only a unit that ends in a deferred document has copies left in flight)
@@ -640,6 +669,25 @@ static cudaError_t launch_sig(const BulkParams &prm_in, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
+// fused LSH insert: default variant only (u32 tokens, safe permutations), one K slice (the whole row in one warp), no pieces
+template <int P, int OCC>
+static cudaError_t launch_sig_lsh(const BulkParams &prm_in, int sm_count, cudaStream_t s) {
+    BulkParams prm = prm_in;
+    int64_t gx = (prm.n_docs + kSigWarps - 1) / kSigWarps;
+    const int64_t gmax = (int64_t)sm_count * OCC;
+    if (gx > gmax) gx = gmax;
+    if (gx < 1) gx = 1;
+    if (prm.docs_per_unit <= 0) {
+        int64_t dpu = prm.n_docs / (gx * kSigWarps * 8);
+        prm.docs_per_unit = (int)(dpu < 1 ? 1 : (dpu > 32 ? 32 : dpu));
+    }
+    prm.long_doc_tokens = 0;
+    cudaError_t e = cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned), s);
+    if (e != cudaSuccess) return e;
+    DSK_LAUNCH((minhash_sig_kernel<P, OCC, false, 0, true>), dim3((unsigned)gx, 1u), kSigWarps * 32, 0, s, prm);
+    return cudaGetLastError();
+}
+
 template <int GEN>
 static cudaError_t launch_sig_k(const BulkParams &prm, int sm_count, cudaStream_t s) {
     if (prm.k <= 32) return launch_sig<1, 4, GEN>(prm, sm_count, s);
@@ -653,6 +701,13 @@ static cudaError_t launch_sig_k(const BulkParams &prm, int sm_count, cudaStream_
 
 // 4 CTAs (16 warps) per SM: 5 and 6 were measured slower (register cap, profiles/r2i_kernel_variants_ab.txt)
 cudaError_t launch_minhash_sig(const BulkParams &prm, int sm_count, cudaStream_t s) {
+    if (prm.lsh_slots != nullptr) {
+        if (prm.gen != 0 || prm.k > 256 || prm.n_peers != 0 || prm.out_is_u64 || prm.lsh_b * prm.lsh_r > prm.k) return cudaErrorInvalidValue;
+        if (prm.k <= 32) return launch_sig_lsh<1, 4>(prm, sm_count, s);
+        if (prm.k <= 64) return launch_sig_lsh<2, 4>(prm, sm_count, s);
+        if (prm.k <= 128) return launch_sig_lsh<4, 4>(prm, sm_count, s);
+        return launch_sig_lsh<8, DSK_SIG_OCC8>(prm, sm_count, s);
+    }
     switch (prm.gen) {
         case 0: return launch_sig_k<0>(prm, sm_count, s);
         case 1: return launch_sig_k<1>(prm, sm_count, s);

@@ -537,6 +537,26 @@ class GpuLSH:
         if keys is not None:
             self.keys.extend(keys)
 
+    def insert_tokens(self, d_tokens, d_offsets, n_tokens: int, permutations: np.ndarray,
+                      keys: Optional[Iterable[Hashable]] = None) -> None:
+        """Append documents given as TOKEN lists (CUDA tensors: uint32/int32 or uint64/int64 hash values, int64 CSR
+        offsets): ``MinHash.bulk`` + ``insert`` of every document (minhash.py:464-489, lsh.py:326-347) in one launch --
+        the signature kernel builds each row straight into the index's storage and the warp that finishes a row does
+        its bucket updates (``dsk_lsh_insert_tokens``).  ``permutations`` is the (2, K) array of ``MinHash.permutations``."""
+        import torch
+        if not d_tokens.is_cuda or not d_offsets.is_cuda or d_tokens.device.index != self.device:
+            raise ValueError("insert_tokens needs CUDA tensors on device %d" % self.device)
+        hp = nv.perm_handle(permutations, self.device)
+        if hp.num_perm != self.h:
+            raise ValueError("Expecting permutations of length %d, got %d" % (self.h, hp.num_perm))
+        n = d_offsets.numel() - 1
+        with torch.cuda.device(self.device):
+            nv.check(nv.load().dsk_lsh_insert_tokens(self._h, hp.handle, d_tokens.data_ptr() if n_tokens else None,
+                                                     int(d_tokens.element_size() == 8), d_offsets.data_ptr(), n, int(n_tokens),
+                                                     torch.cuda.current_stream().cuda_stream))
+        if keys is not None:
+            self.keys.extend(keys)
+
     def query(self, sig, to_host: bool = True):
         """Candidates of every row of ``sig``: ``(ptr int64[Q+1], idx int32[total])``."""
         import torch

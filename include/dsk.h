@@ -212,6 +212,12 @@ DSK_API int dsk_wmh_minhash(const dsk_wmh *g, const float *d_v, int64_t n, int64
  * numbered 0..n_docs-1 in insertion order (the host layer maps numbers to user keys).  Buckets
  * are exact: two documents meet iff a band's r-tuple is equal, as with the reference's byte keys.
  *   dsk_lsh_insert       append n signatures ([n, num_perm] u32) to the index
+ *   dsk_lsh_insert_tokens  the same from TOKENS: builds the n documents' signatures (dsk_minhash_bulk's kernel) straight into
+ *                        the index's own signature storage and inserts each document in the same launch -- the warp that
+ *                        finishes a row does its b bucket updates, whose DRAM latency hides behind the other warps'
+ *                        integer work; the signature matrix is never read back.  (MinHash.bulk + MinHashLSH.insert per
+ *                        document, minhash.py:464-489 + lsh.py:326-347.)  Fused for u32 tokens, a handle with
+ *                        n_unsafe == 0 and num_perm <= 256; any other input runs the two kernels one after the other.
  *   dsk_lsh_query_count  d_counts[q] = number of distinct candidates of query q
  *   dsk_exclusive_scan   d_out[0..n] = exclusive prefix sums of d_in[0..n-1] (d_out[n] = total);
  *                        d_scratch holds at least n/1024 + 2 int64
@@ -222,6 +228,8 @@ DSK_API int dsk_lsh_create(int num_perm, int b, int r, int64_t capacity_docs, in
 DSK_API void dsk_lsh_destroy(dsk_lsh *ix);
 DSK_API int dsk_lsh_size(const dsk_lsh *ix, int64_t *n_docs, int64_t *capacity_docs);
 DSK_API int dsk_lsh_insert(dsk_lsh *ix, const uint32_t *d_sig, int64_t n, void *stream);
+DSK_API int dsk_lsh_insert_tokens(dsk_lsh *ix, const dsk_perm *perm, const void *d_tokens, int token_is_u64,
+                                  const int64_t *d_offsets, int64_t n_docs, int64_t n_tokens, void *stream);
 DSK_API int dsk_lsh_query_count(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, int64_t *d_counts, void *stream);
 DSK_API int dsk_lsh_query_fill(const dsk_lsh *ix, const uint32_t *d_qsig, int64_t nq, const int64_t *d_ptr,
                                int32_t *d_idx, void *stream);

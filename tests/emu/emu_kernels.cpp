@@ -152,6 +152,33 @@ extern "C" int emu_lsh_insert(void *h, const uint32_t *sig, int64_t n, int sm_co
     ix->n_docs += n;
     return rc;
 }
+// the fused route of dsk_lsh_insert_tokens: signature kernel with the insert epilogue, rows built in the index's storage
+extern "C" int emu_lsh_insert_tokens(void *h, const uint32_t *tokens, const int64_t *offsets, int64_t n_docs, const uint64_t *a,
+                                     const uint64_t *b, int k, int docs_per_unit, int grid_x) {
+    EmuLsh *ix = static_cast<EmuLsh *>(h);
+    if (ix->n_docs + n_docs > ix->dev.cap_docs || k != ix->dev.k) return -1;
+    const int kpad = (k + 255) / 256 * 256;
+    std::vector<uint32_t> tab((size_t)6 * kpad);
+    for (int i = 0; i < kpad; ++i) {
+        const int s = i % k;
+        tab[i] = (uint32_t)a[s]; tab[kpad + i] = (uint32_t)(a[s] >> 32);
+        tab[2 * kpad + i] = (uint32_t)b[s]; tab[3 * kpad + i] = (uint32_t)(b[s] >> 32);
+        tab[4 * kpad + i] = (uint32_t)b[s] + 7u; tab[5 * kpad + i] = (uint32_t)b[s] + 8u;
+    }
+    std::vector<unsigned> counters(64, 0u);
+    dsk::BulkParams prm{};
+    prm.tokens = tokens; prm.offsets = offsets; prm.n_docs = n_docs; prm.n_tokens = offsets[n_docs];
+    prm.a_lo = tab.data(); prm.a_hi = tab.data() + kpad; prm.b_lo = tab.data() + 2 * kpad; prm.b_hi = tab.data() + 3 * kpad;
+    prm.b_lo7 = tab.data() + 4 * kpad; prm.b_lo8 = tab.data() + 5 * kpad; prm.gen = 0;
+    prm.k = k; prm.out = ix->dev.sig + ix->n_docs * k; prm.out_is_u64 = 0; prm.work_counter = counters.data();
+    prm.docs_per_unit = docs_per_unit;
+    prm.lsh_slots = ix->dev.slots; prm.lsh_next = ix->dev.next; prm.lsh_cap_slots = ix->dev.cap_slots;
+    prm.lsh_doc0 = ix->n_docs; prm.lsh_b = ix->dev.b; prm.lsh_r = ix->dev.r;
+    const int rc = dsk::launch_minhash_sig(prm, grid_x, nullptr);
+    ix->n_docs += n_docs;
+    return rc;
+}
+extern "C" const uint32_t *emu_lsh_rows(void *h) { return static_cast<EmuLsh *>(h)->dev.sig; }
 // count -> exclusive scan -> fill, the sequence GpuLSH.query runs; ptr has nq + 1 entries, idx must hold ptr[nq]
 extern "C" int64_t emu_lsh_query_count(void *h, const uint32_t *q, int64_t nq, int64_t *ptr, int sm_count) {
     EmuLsh *ix = static_cast<EmuLsh *>(h);

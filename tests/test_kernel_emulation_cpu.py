@@ -727,3 +727,64 @@ def test_general_variants_long_documents_in_pieces(emu, gen):
         assert lib.emu_minhash_sig_long(tok.ctypes.data, off.ctypes.data, n, a.ctypes.data, b.ctypes.data, k, None, 0, 0,
                                         out.ctypes.data, 0, dpu, gx, 100, 5, None, gen) == 0
         assert np.array_equal(out, want), (gen, dpu, gx)
+
+
+@pytest.mark.parametrize("k,b,r", [(128, 32, 4), (256, 17, 15), (64, 9, 7), (16, 4, 4)])
+def test_fused_lsh_insert_from_tokens_vs_dict_oracle(emu, k, b, r):
+    """signature_kernel.cu template LSH (dsk_lsh_insert_tokens' fused route): the warp that finishes a document inserts
+    it.  Token lists with planted near-duplicates and exact duplicates (so buckets have several members and chains get
+    contended), empty and ragged documents, two batches (the second one lands behind the first in the index), several
+    unit sizes; afterwards the index's rows equal the oracle's signatures and every query's candidate set equals the
+    reference's dict buckets (oracle DictLSH = lsh.py:326-347, :370-432)."""
+    lib = emu.lib
+    lib.emu_lsh_create.restype = ctypes.c_void_p
+    lib.emu_lsh_query_count.restype = ctypes.c_int64
+    lib.emu_lsh_rows.restype = ctypes.c_void_p
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.emu_lsh_insert_tokens.argtypes = [vp, vp, vp, i64, vp, vp, ci, ci, ci]
+    rs = np.random.RandomState(k + b)
+    n = 150
+    docs = []
+    for i in range(n):
+        if i % 5 == 3 and i > 10:                       # near-duplicate of an earlier document: a few tokens resampled
+            base = docs[int(rs.randint(0, i))].copy()
+            if len(base):
+                base[rs.randint(0, len(base), size=max(1, len(base) // 40))] = rs.randint(0, 1 << 32, dtype=np.uint64)
+            docs.append(base)
+        elif i % 11 == 7:
+            docs.append(docs[i - 1].copy())             # exact duplicate
+        else:
+            docs.append(rs.randint(0, 1 << 32, size=int(rs.choice([0, 3, 40, 64, 130, 256, 300])), dtype=np.uint64).astype(np.uint32))
+    docs = [np.asarray(d, dtype=np.uint32) for d in docs]
+    perms = o.init_permutations(k, 2)
+    a, bb = np.ascontiguousarray(perms[0]), np.ascontiguousarray(perms[1])
+    ref = o.DictLSH(k, b, r)
+    want_rows = []
+    h = ctypes.c_void_p(lib.emu_lsh_create(k, b, r, ctypes.c_int64(n + 5)))
+    for (lo, hi), (dpu, gx) in zip(((0, 60), (60, n)), ((3, 1), (32, 2))):
+        part = docs[lo:hi]
+        off = np.zeros(len(part) + 1, dtype=np.int64)
+        np.cumsum([len(d) for d in part], out=off[1:])
+        tok = np.concatenate(part + [np.zeros(4, np.uint32)])[:int(off[-1])]
+        tok = np.ascontiguousarray(tok)
+        sig = oc.minhash_bulk_u32tok(tok, off, perms)
+        want_rows.append(sig)
+        for i, row in enumerate(sig):
+            ref.insert(lo + i, row.astype(np.uint64))
+        assert lib.emu_lsh_insert_tokens(h, tok.ctypes.data, off.ctypes.data, len(part), a.ctypes.data, bb.ctypes.data, k, dpu, gx) == 0
+    want_rows = np.concatenate(want_rows)
+    rows = np.ctypeslib.as_array(ctypes.cast(lib.emu_lsh_rows(h), ctypes.POINTER(ctypes.c_uint32)), shape=(n + 5, k))[:n]
+    assert np.array_equal(rows, want_rows)
+    q = np.ascontiguousarray(want_rows[::2])
+    nq = len(q)
+    ptr = np.zeros(nq + 1, dtype=np.int64)
+    total = lib.emu_lsh_query_count(h, _ptr(q), ctypes.c_int64(nq), _ptr(ptr), 2)
+    idx = np.full(max(total, 1), -1, dtype=np.int32)
+    assert lib.emu_lsh_query_fill(h, _ptr(q), ctypes.c_int64(nq), _ptr(ptr), _ptr(idx), 2) == 0
+    multi = 0
+    for j in range(nq):
+        got = sorted(idx[ptr[j]:ptr[j + 1]].tolist())
+        assert got == sorted(ref.query(q[j].astype(np.uint64))), j
+        multi += len(got) > 1
+    assert multi >= 5            # the planted duplicates really share buckets
+    lib.emu_lsh_destroy(h)

@@ -113,3 +113,64 @@ def test_end_to_end_minhash_to_lsh(dsk):
         assert set(res[i]) == ref.query(sig[i].astype(np.uint64))
     found = sum(1 for i in range(0, 500, 5) if f"doc{i + 1}" in res[i])
     assert found >= 80   # ~95 % similar pairs collide in some band with overwhelming probability
+
+
+@pytest.mark.parametrize("k,params", [(128, None), (256, (17, 15)), (64, (9, 7)), (300, (20, 15))])
+def test_fused_insert_from_tokens_equals_the_two_step_flow(dsk, k, params):
+    """``GpuLSH.insert_tokens`` (dsk_lsh_insert_tokens: the signature kernel with the fused insert epilogue; num_perm = 300
+    and 64-bit tokens take its two-kernel route) against signatures-then-insert and against the reference's dict buckets
+    (oracle DictLSH = lsh.py:326-347, :370-432): same candidate sets for every query."""
+    import torch
+    rs = np.random.RandomState(k)
+    n = 3000
+    docs = []
+    for i in range(n):
+        if i % 4 == 1 and i > 8:
+            d = docs[int(rs.randint(0, i))].copy()
+            if len(d):
+                d[rs.randint(0, len(d), size=max(1, len(d) // 30))] = rs.randint(0, 2 ** 32, dtype=np.uint64)
+            docs.append(d)
+        elif i % 9 == 5:
+            docs.append(docs[i - 1].copy())
+        else:
+            docs.append(rs.randint(0, 2 ** 32, size=int(rs.choice([0, 5, 64, 100, 256, 700, 5000 if i % 500 == 0 else 33])),
+                                   dtype=np.uint64).astype(np.uint32))
+    docs = [np.asarray(d, dtype=np.uint32) for d in docs]
+    P = o.init_permutations(k, 3)
+    kw = dict(params=params) if params else dict(threshold=0.8)
+    for u64 in (False, True):
+        fused = dsk.GpuLSH(num_perm=k, capacity=n, **kw)
+        plain = dsk.GpuLSH(num_perm=k, capacity=n, **kw)
+        ref = o.DictLSH(k, fused.b, fused.r)
+        sigs = []
+        for lo, hi in ((0, 1000), (1000, n)):        # two batches: the second lands behind the first
+            part = docs[lo:hi]
+            off = np.zeros(len(part) + 1, dtype=np.int64)
+            np.cumsum([len(d) for d in part], out=off[1:])
+            tok = np.ascontiguousarray(np.concatenate(part))
+            if u64:
+                tok = tok.astype(np.uint64) | (np.uint64(1) << np.uint64(40))
+            d_tok = torch.from_numpy(tok.view(np.int64 if u64 else np.int32)).cuda()
+            d_off = torch.from_numpy(off).cuda()
+            fused.insert_tokens(d_tok, d_off, len(tok), P)
+            sig = dsk.engine.bulk_signatures_device(d_tok, d_off, len(tok), P)
+            plain.insert(sig)
+            sigs.append(sig.cpu().numpy().view(np.uint32))
+        sig = np.concatenate(sigs)
+        assert len(fused) == n and len(plain) == n
+        for i, row in enumerate(sig):
+            ref.insert(i, row.astype(np.uint64))
+        q = sig[::3]
+        p1, i1 = fused.query(q)
+        p2, i2 = plain.query(q)
+        assert np.array_equal(p1, p2)
+        multi = 0
+        for j in range(len(q)):
+            a = sorted(i1[p1[j]:p1[j + 1]].tolist())
+            assert a == sorted(i2[p2[j]:p2[j + 1]].tolist()) and a == sorted(ref.query(q[j].astype(np.uint64))), (u64, j)
+            multi += len(a) > 1
+        assert multi > 100
+    with pytest.raises(ValueError):
+        fused.insert_tokens(d_tok, d_off, len(tok), o.init_permutations(k + 1, 3))
+    with pytest.raises(ValueError):
+        fused.insert_tokens(d_tok, d_off, len(tok), P)      # capacity exceeded

@@ -59,7 +59,26 @@ def c3(n_docs, t=128, k=256, n_query=100_000):
     e1.record()
     torch.cuda.synchronize()
     ms_ins = e0.elapsed_time(e1)
+    # fused: tokens -> signatures in the index's storage + bucket updates in ONE launch (GpuLSH.insert_tokens); three fresh
+    # indexes, the first one warms the kernel up; candidates of the same queries must be identical to the two-step index
+    ms_fused = []
+    fused = None
+    for rep in range(3):
+        del fused
+        fused = dsk.GpuLSH(threshold=0.8, num_perm=k, capacity=n_docs)
+        torch.cuda.synchronize()
+        e0.record()
+        fused.insert_tokens(tok.view(-1), off, n_docs * t, perms)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_fused.append(e0.elapsed_time(e1))
     q = sig[torch.randint(0, n_docs, (n_query,), device="cuda", generator=g)]
+    pf, xf = fused.query(q[:20_000], to_host=False)
+    pp, xp = lsh.query(q[:20_000], to_host=False)
+    same = bool(torch.equal(pf, pp)) and bool(torch.equal(
+        torch.sort(xf.long() + torch.repeat_interleave(torch.arange(20_000, device="cuda"), pf[1:] - pf[:-1]) * n_docs)[0],
+        torch.sort(xp.long() + torch.repeat_interleave(torch.arange(20_000, device="cuda"), pp[1:] - pp[:-1]) * n_docs)[0]))
+    del fused
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ptr, idx = lsh.query(q, to_host=False)
@@ -80,6 +99,8 @@ def c3(n_docs, t=128, k=256, n_query=100_000):
     return {"config": "C3 (1 GPU)", "docs": n_docs, "tokens": t, "num_perm": k, "b": lsh.b, "r": lsh.r,
             "signature_ms": ms_sig, "signatures_per_s": n_docs / ms_sig * 1e3,
             "lsh_insert_ms": ms_ins, "lsh_insert_docs_per_s": n_docs / ms_ins * 1e3,
+            "fused_signatures_plus_insert_ms": min(ms_fused[1:]), "fused_runs_ms": ms_fused,
+            "two_step_signatures_plus_insert_ms": ms_sig + ms_ins, "fused_candidates_identical": same,
             "lsh_query_ms": ms_q, "queries": n_query, "lsh_queries_per_s": n_query / ms_q * 1e3,
             "candidates_total": int(ptr[-1].item()),
             "cpu_oracle_insert_us_per_doc": cpu_ins * 1e6, "cpu_oracle_query_us_per_doc": cpu_q * 1e6}
