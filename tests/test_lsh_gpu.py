@@ -115,14 +115,14 @@ def test_end_to_end_minhash_to_lsh(dsk):
     assert found >= 80   # ~95 % similar pairs collide in some band with overwhelming probability
 
 
-@pytest.mark.parametrize("k,params", [(128, None), (256, (17, 15)), (64, (9, 7)), (300, (20, 15))])
+@pytest.mark.parametrize("k,params", [(128, (9, 13)), (256, (17, 15)), (64, (9, 7)), (300, (20, 15))])
 def test_fused_insert_from_tokens_equals_the_two_step_flow(dsk, k, params):
     """``GpuLSH.insert_tokens`` (dsk_lsh_insert_tokens: the signature kernel with the fused insert epilogue; num_perm = 300
     and 64-bit tokens take its two-kernel route) against signatures-then-insert and against the reference's dict buckets
     (oracle DictLSH = lsh.py:326-347, :370-432): same candidate sets for every query."""
     import torch
     rs = np.random.RandomState(k)
-    n = 3000
+    n = 1500
     docs = []
     for i in range(n):
         if i % 4 == 1 and i > 8:
@@ -137,13 +137,13 @@ def test_fused_insert_from_tokens_equals_the_two_step_flow(dsk, k, params):
                                    dtype=np.uint64).astype(np.uint32))
     docs = [np.asarray(d, dtype=np.uint32) for d in docs]
     P = o.init_permutations(k, 3)
-    kw = dict(params=params) if params else dict(threshold=0.8)
+    kw = dict(params=params)
     for u64 in (False, True):
         fused = dsk.GpuLSH(num_perm=k, capacity=n, **kw)
         plain = dsk.GpuLSH(num_perm=k, capacity=n, **kw)
         ref = o.DictLSH(k, fused.b, fused.r)
         sigs = []
-        for lo, hi in ((0, 1000), (1000, n)):        # two batches: the second lands behind the first
+        for lo, hi in ((0, 600), (600, n)):        # two batches: the second lands behind the first
             part = docs[lo:hi]
             off = np.zeros(len(part) + 1, dtype=np.int64)
             np.cumsum([len(d) for d in part], out=off[1:])
@@ -169,7 +169,7 @@ def test_fused_insert_from_tokens_equals_the_two_step_flow(dsk, k, params):
             a = sorted(i1[p1[j]:p1[j + 1]].tolist())
             assert a == sorted(i2[p2[j]:p2[j + 1]].tolist()) and a == sorted(ref.query(q[j].astype(np.uint64))), (u64, j)
             multi += len(a) > 1
-        assert multi > 100
+        assert multi > 50
     with pytest.raises(ValueError):
         fused.insert_tokens(d_tok, d_off, len(tok), o.init_permutations(k + 1, 3))
     with pytest.raises(ValueError):
