@@ -326,14 +326,20 @@ __global__ void __launch_bounds__(kSigWarps * 32, OCC) minhash_sig_kernel(const 
                             const int i = i0 + lane;
                             bool keep = i < len;
                             uint32_t t = kEmptySlot, thi = kEmptySlot;
-                            if constexpr (TW == 2) {   // the same table as 512 64-bit slots; identity = the whole 64-bit token
+                            if constexpr (TW == 2) {
+                                // 64-bit tokens: the slot holds the POSITION of the last token that went through it (a 32-bit
+                                // exchange -- 64-bit shared-memory atomics are far slower), identity = the whole token, read
+                                // back from the ring: dropped iff the token at the returned position equals this one
                                 if (keep) {
-                                    const uint2 t2 = reinterpret_cast<const uint2 *>(ring)[((rpos >> 1) + (uint32_t)i) & (kRingTok / 2 - 1)];
+                                    const uint2 *r2 = reinterpret_cast<const uint2 *>(ring);
+                                    const uint2 t2 = r2[((rpos >> 1) + (uint32_t)i) & (kRingTok / 2 - 1)];
                                     t = t2.x; thi = t2.y;
+                                    const uint32_t prev = atomicExch(&tab[((t ^ (thi * 0x85EBCA6Bu)) * 0x9E3779B1u) >> 22], (uint32_t)i);
+                                    if (prev != kEmptySlot) {
+                                        const uint2 o2 = r2[((rpos >> 1) + prev) & (kRingTok / 2 - 1)];
+                                        keep = o2.x != t || o2.y != thi;
+                                    }
                                 }
-                                const unsigned long long t64 = ((unsigned long long)thi << 32) | t;
-                                if (t64 != ~0ull)
-                                    keep = atomicExch(reinterpret_cast<unsigned long long *>(tab) + (((t ^ (thi * 0x85EBCA6Bu)) * 0x9E3779B1u) >> 23), t64) != t64;
                             } else {
                                 if (keep) t = ring[(rpos + (uint32_t)i) & (kRingTok - 1)];
                                 if (t != kEmptySlot) keep = atomicExch(&tab[(t * 0x9E3779B1u) >> 22], t) != t;

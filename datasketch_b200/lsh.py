@@ -306,6 +306,27 @@ class MinHashLSH:
             layout.add(stored, hs)
         return layout
 
+    def export_cassandra(self, basename: bytes, prepickle: Optional[bool] = None):
+        """This index in the reference's Cassandra layout (``storage_export.CassandraLayout``; lsh.py:191-200,
+        storage.py:262-819): the rows ``MinHashLSH(storage_config={"type": "cassandra", "basename": basename, ...})`` would
+        have written after the same inserts, in the same order.  ``prepickle`` defaults to False as for Cassandra in the
+        reference (lsh.py:182): keys must then be bytes."""
+        from .storage_export import CassandraLayout
+        prepickle = False if prepickle is None else prepickle
+        layout = CassandraLayout(basename, self.b)
+        for key in self.keys.keys():
+            hs = list(self.keys.get(key))
+            stored = key
+            if self.prepickle:                     # this index already holds pickled keys
+                if not prepickle:
+                    stored = pickle.loads(key)
+            elif prepickle:
+                stored = pickle.dumps(key)
+            if not isinstance(stored, bytes):
+                raise TypeError("prepickle=False requires bytes keys for non-dict storage, got %s" % type(stored).__name__)
+            layout.add(stored, hs)
+        return layout
+
     # -- merge (lsh.py:233-251, :349-368) -------------------------------------------------------------------------
     def merge(self, other: "MinHashLSH", check_overlap: bool = False):
         self._merge(other, check_overlap=check_overlap, buffer=False)

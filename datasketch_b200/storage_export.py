@@ -16,9 +16,22 @@ band's r hash values as big-endian uint64 bytes (``_H``, lsh.py:537-538), option
 dictionary glue on the host.  ``RedisLayout`` holds the three Redis data types as dicts, can replay itself as
 commands into any client with the redis-py pipeline interface, and compares equal to the state the reference itself
 produces on an in-memory stand-in (fixture tests/golden/storage.npz).
+
+``MinHashLSH`` over Cassandra (datasketch/storage.py:262-819) uses one table per container,
+
+    table   "lsh_" + basename + "_keys"                              rows (key = <key>, value = H_i, ts)   INSERT, storage.py:375, :505-516
+    table   "lsh_" + basename + "_bucket_" + hexlify(pack(">H", i))  rows (key = <H>,   value = <key>, ts) UPDATE (upsert), :369-373, :518-534
+
+``(key blob, value blob, ts bigint, PRIMARY KEY (key, value)) WITH CLUSTERING ORDER BY (value DESC)`` (:324-331), ``ts`` from
+a per-table monotonic generator (:384) -- so a document's band keys are recovered in band order by sorting on ``ts``, and a
+repeated (key, value) pair keeps one row.  ``prepickle`` defaults to False for Cassandra (lsh.py:182): keys must be bytes
+unless ``prepickle=True``.  ``CassandraLayout`` holds the rows per table and replays itself into a cassandra-driver session;
+it compares equal (rows and their ``ts`` order) to what the reference's own storage code wrote on an in-memory stand-in
+(fixture tests/golden/storage_cassandra.npz).
 """
 from __future__ import annotations
 
+import binascii
 import pickle
 import struct
 from typing import Callable, Dict, Hashable, Iterator, List, Optional, Sequence, Set, Tuple
@@ -106,6 +119,105 @@ def redis_layout(keys: Sequence[Hashable], signatures, b: int, r: int, basename:
     if len(keys) != n:
         raise ValueError("keys and signatures differ in length")
     layout = RedisLayout(basename, b)
+    if n == 0:
+        return layout
+    width = 8 * r
+    raw = codec.band_keys(sig, b, r).cpu().numpy().reshape(n, b * width).tobytes()
+    for i, key in enumerate(keys):
+        if prepickle:
+            key = pickle.dumps(key)
+        elif not isinstance(key, bytes):
+            raise TypeError(f"prepickle=False requires bytes keys for non-dict storage, got {type(key).__name__}. "
+                            "Either pass bytes keys or use prepickle=True for automatic serialization.")
+        base = i * b * width
+        hs = [raw[base + j * width: base + (j + 1) * width] for j in range(b)]
+        if hashfunc is not None:
+            hs = [hashfunc(h) for h in hs]
+        layout.add(key, hs)
+    return layout
+
+
+# ---- Cassandra ---------------------------------------------------------------------------------------------------------
+CASSANDRA_CREATE_TABLE = ("CREATE TABLE IF NOT EXISTS {} ( key blob, value blob, ts bigint, PRIMARY KEY (key, value) ) "
+                          "WITH CLUSTERING ORDER BY (value DESC)")                               # storage.py:324-331
+CASSANDRA_INSERT = "INSERT INTO {} (key, value, ts) VALUES (?, ?, ?)"                              # storage.py:375
+
+
+def cassandra_table_name(container_name: bytes) -> str:
+    """storage.py:398-402: bucket containers get their 2-byte band number hex-encoded, every table the ``lsh_`` prefix."""
+    name = container_name
+    if b"bucket" in name:
+        basename, _, ret = name.split(b"_", 2)
+        name = basename + b"_bucket_" + binascii.hexlify(ret)
+    return "lsh_" + name.decode("ascii")
+
+
+class CassandraLayout:
+    """The Cassandra tables of one MinHashLSH index: ``tables[name]`` maps ``(key, value)`` to ``ts`` (1, 2, ... in the
+    order the reference's client would have written the rows of that table)."""
+
+    def __init__(self, basename: bytes, b: int):
+        self.basename, self.b = bytes(basename), int(b)
+        self.keys_table = cassandra_table_name(keys_container_name(self.basename))
+        self.bucket_tables = [cassandra_table_name(bucket_container_name(self.basename, i)) for i in range(self.b)]
+        self.tables: Dict[str, Dict[Tuple[bytes, bytes], int]] = {t: {} for t in [self.keys_table] + self.bucket_tables}
+        self._ts: Dict[str, int] = {t: 0 for t in self.tables}
+
+    def _put(self, table: str, key: bytes, value: bytes) -> None:
+        self._ts[table] += 1
+        self.tables[table][(key, value)] = self._ts[table]        # PRIMARY KEY (key, value): a repeat overwrites ts
+
+    def add(self, key: bytes, band_keys: Sequence[bytes]) -> None:
+        """What ``MinHashLSH._insert`` writes for one document (lsh.py:344-347 over storage.py:771-774, :813-816)."""
+        if len(band_keys) != self.b:
+            raise ValueError("expected %d band keys, got %d" % (self.b, len(band_keys)))
+        for h in band_keys:
+            self._put(self.keys_table, key, h)
+        for table, h in zip(self.bucket_tables, band_keys):
+            self._put(table, h, key)
+
+    def ddl(self) -> List[str]:
+        return [CASSANDRA_CREATE_TABLE.format(t) for t in self.bucket_tables + [self.keys_table]]   # lsh.py:191-200 order
+
+    def statements(self) -> Iterator[Tuple[str, Tuple[bytes, bytes, int]]]:
+        """``(cql, (key, value, ts))`` per row, tables in creation order, rows in ``ts`` order."""
+        for t in self.bucket_tables + [self.keys_table]:
+            cql = CASSANDRA_INSERT.format(t)
+            for (key, value), ts in sorted(self.tables[t].items(), key=lambda kv: kv[1]):
+                yield cql, (key, value, ts)
+
+    def write(self, session) -> int:
+        """Create the tables and insert every row through a cassandra-driver style session (``execute``, ``prepare``)."""
+        for q in self.ddl():
+            session.execute(q)
+        prepared, n = {}, 0
+        for cql, params in self.statements():
+            st = prepared.get(cql)
+            if st is None:
+                st = prepared[cql] = session.prepare(cql)
+            session.execute(st, params)
+            n += 1
+        return n
+
+    def canonical(self):
+        """Comparable form: per table the (key, value) rows in ``ts`` order (what the golden fixture stores)."""
+        return {t: [kv for kv, _ in sorted(rows.items(), key=lambda x: x[1])] for t, rows in self.tables.items()}
+
+    def __eq__(self, other):
+        return isinstance(other, CassandraLayout) and self.canonical() == other.canonical()
+
+
+def cassandra_layout(keys: Sequence[Hashable], signatures, b: int, r: int, basename: bytes, prepickle: bool = False,
+                     hashfunc: Optional[Callable[[bytes], bytes]] = None) -> CassandraLayout:
+    """Cassandra layout of ``MinHashLSH(params=(b, r), storage_config={"type": "cassandra", "basename": basename, ...})``
+    after ``insert(keys[i], signature i)`` for every row of ``signatures``; band keys from one ``dsk_band_keys`` launch."""
+    from . import codec
+    from .lsh import _signature_matrix
+    sig = _signature_matrix(signatures) if isinstance(signatures, np.ndarray) or not hasattr(signatures, "is_cuda") else signatures
+    n = int(sig.shape[0])
+    if len(keys) != n:
+        raise ValueError("keys and signatures differ in length")
+    layout = CassandraLayout(basename, b)
     if n == 0:
         return layout
     width = 8 * r

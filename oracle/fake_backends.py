@@ -1,7 +1,7 @@
-"""TEST INFRASTRUCTURE ONLY -- in-memory stand-ins for two optional third-party packages the reference imports
-(`redis`, `pybloomfilter`; neither is installed here), so that oracle/gen_golden.py can run the reference's OWN
-storage / LSHBloom code paths (datasketch/storage.py:819-1049, datasketch/lsh_bloom.py:53-380) and record what they
-write.  They implement just the calls those code paths make and keep every value they are given.
+"""TEST INFRASTRUCTURE ONLY -- in-memory stand-ins for three optional third-party packages the reference imports
+(`redis`, `cassandra` (cassandra-driver), `pybloomfilter`; none is installed here), so that oracle/gen_golden.py can run the
+reference's OWN storage / LSHBloom code paths (datasketch/storage.py:262-1049, datasketch/lsh_bloom.py:53-380) and record
+what they write.  They implement just the calls those code paths make and keep every value they are given.
 
     install()   # before `import datasketch`: puts the fakes into sys.modules
 """
@@ -12,6 +12,7 @@ import types
 
 DB = {"hash": {}, "list": {}, "set": {}}      # the one fake Redis database: name -> dict / list / set
 BLOOM_ADDS = []                                # (filename or None, value) for every BloomFilter.add
+CQL = {"ddl": [], "tables": {}}                # the one fake Cassandra keyspace: executed DDL strings; table -> {(key, value): ts}
 
 
 def _b(x):
@@ -86,7 +87,85 @@ class _BloomFilter:
         return cls(filename=fname)
 
 
+class _Prepared:
+    """A prepared statement: the CQL text, its kind and its table (the reference formats the table name in)."""
+    def __init__(self, query):
+        import re
+        self.query = " ".join(query.split())
+        self.kind = self.query.split(" ", 1)[0].upper()
+        m = re.search(r"(?:INTO|UPDATE|FROM)\s+(\S+)", self.query)
+        self.table = m.group(1) if m else None
+
+
+class _Row:
+    def __init__(self, key, value, ts):
+        self.key, self.value, self.ts = key, value, ts
+
+
+class _Session:
+    """cassandra.cluster.Session, as far as datasketch/storage.py:262-650 uses it."""
+    keyspace = None
+
+    def execute(self, query, parameters=None):
+        if isinstance(query, _Prepared):
+            return self._run(query, parameters)
+        CQL["ddl"].append(" ".join(query.split()))
+        return []
+
+    def set_keyspace(self, keyspace):
+        self.keyspace = keyspace
+
+    def prepare(self, query):
+        return _Prepared(query)
+
+    def _run(self, st, params):
+        rows = CQL["tables"].setdefault(st.table, {})
+        if st.kind == "INSERT":                      # (key, value, ts)
+            rows[(_b(params[0]), _b(params[1]))] = params[2]
+            return []
+        if st.kind == "UPDATE":                      # SET ts = ? WHERE key = ? AND value = ?
+            rows[(_b(params[1]), _b(params[2]))] = params[0]
+            return []
+        if st.kind == "SELECT":                      # WHERE key = ?   (clustering order: value DESC)
+            key = _b(params[0])
+            out = [_Row(k, v, ts) for (k, v), ts in rows.items() if k == key]
+            out.sort(key=lambda r: r.value, reverse=True)
+            return out[:1] if "LIMIT 1" in st.query else out
+        raise NotImplementedError(st.query)
+
+
+class _Cluster:
+    def __init__(self, seeds=None, **kwargs):
+        pass
+
+    def connect(self):
+        return _Session()
+
+
+class _MonotonicTimestampGenerator:
+    def __init__(self):
+        self.t = 0
+
+    def __call__(self):
+        self.t += 1
+        return self.t
+
+
+def _execute_concurrent(session, statements_and_parameters, concurrency=100, **kwargs):
+    return [(True, session.execute(st, params)) for st, params in statements_and_parameters]
+
+
 def install():
+    cas = types.ModuleType("cassandra")
+    cas_cluster = types.ModuleType("cassandra.cluster")
+    cas_cluster.Cluster = _Cluster
+    cas_cluster.MonotonicTimestampGenerator = _MonotonicTimestampGenerator
+    cas_conc = types.ModuleType("cassandra.concurrent")
+    cas_conc.execute_concurrent = _execute_concurrent
+    cas.cluster, cas.concurrent = cas_cluster, cas_conc
+    sys.modules["cassandra"] = cas
+    sys.modules["cassandra.cluster"] = cas_cluster
+    sys.modules["cassandra.concurrent"] = cas_conc
     redis = types.ModuleType("redis")
     client = types.ModuleType("redis.client")
     client.Pipeline = _Pipeline
@@ -103,3 +182,5 @@ def install():
 def reset():
     DB["hash"].clear(); DB["list"].clear(); DB["set"].clear()
     del BLOOM_ADDS[:]
+    del CQL["ddl"][:]
+    CQL["tables"].clear()

@@ -413,6 +413,33 @@ def gen_storage():
     np.savez_compressed(os.path.join(OUT, "storage.npz"), **d)
 
 
+def gen_storage_cassandra():
+    """MinHashLSH over the reference's Cassandra storage (storage.py:262-819) on the cassandra-driver stand-in: the rows
+    of every table in the order they were written (ts), the DDL, and a query answered from those rows."""
+    import pickle
+    sig = np.load(os.path.join(OUT, "lsh.npz"))["sig"]
+    d = {}
+    cases = {"pickled": dict(prepickle=True, keys=[("doc", i) for i in range(120)]),
+             "bytes": dict(prepickle=None, keys=[b"k%04d" % i for i in range(120)])}
+    for name, c in cases.items():
+        fake_backends.reset()
+        cfg = {"type": "cassandra", "basename": b"gpuidx",
+               "cassandra": {"seeds": ["nowhere"], "keyspace": "lsh_test",
+                             "replication": {"class": "SimpleStrategy", "replication_factor": "1"},
+                             "drop_keyspace": False, "drop_tables": False}}
+        lsh = MinHashLSH(threshold=0.8, num_perm=128, prepickle=c["prepickle"], storage_config=cfg)
+        for key, row in zip(c["keys"], sig):
+            lsh.insert(key, LeanMinHash(seed=1, hashvalues=row.astype(np.uint64)))
+        state = {t: [kv for kv, _ in sorted(rows.items(), key=lambda x: x[1])] for t, rows in fake_backends.CQL["tables"].items()}
+        d[name + "_state"] = np.frombuffer(pickle.dumps(state, protocol=4), dtype=np.uint8)
+        d[name + "_ddl"] = np.frombuffer(pickle.dumps([q for q in fake_backends.CQL["ddl"] if q.startswith("CREATE TABLE")],
+                                                      protocol=4), dtype=np.uint8)
+        d[name + "_b_r"] = np.array([lsh.b, lsh.r], dtype=np.int64)
+        q = sorted(lsh.query(LeanMinHash(seed=1, hashvalues=sig[0].astype(np.uint64))), key=repr)
+        d[name + "_query0"] = np.frombuffer(pickle.dumps(q, protocol=4), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "storage_cassandra.npz"), **d)
+
+
 if __name__ == "__main__":
     print("reference:", datasketch.__file__)
     gen_minhash()
@@ -426,5 +453,6 @@ if __name__ == "__main__":
     gen_hashes()
     gen_bloom()
     gen_storage()
+    gen_storage_cassandra()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

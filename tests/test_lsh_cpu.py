@@ -137,3 +137,44 @@ def test_prepickle_hashfunc_and_weighted(dsk, golden):
     lw = dsk.WeightedMinHashLSH(threshold=0.5, num_perm=4, params=(2, 2))
     lw.insert("w", w)
     assert lw.query(w) == ["w"] and all(len(H) == 2 * 2 * 8 for H in lw.keys["w"])
+
+
+def test_cassandra_layout_equals_what_the_reference_wrote(dsk, golden):
+    """storage_export.CassandraLayout / MinHashLSH.export_cassandra against the rows the reference's OWN Cassandra storage
+    code (datasketch/storage.py:262-819) wrote on an in-memory cassandra-driver stand-in (oracle/gen_golden.py,
+    tests/golden/storage_cassandra.npz): the same tables, the same (key, value) rows, in the same ts order; replayed into a
+    session with the driver's interface, the state is the reference's again."""
+    from datasketch_b200 import storage_export as se
+    sig = golden("lsh")["sig"]
+    s = golden("storage_cassandra")
+    for name, mk, prepickle in (("pickled", lambda i: ("doc", i), True), ("bytes", lambda i: b"k%04d" % i, False)):
+        state = pickle.loads(s[name + "_state"].tobytes())
+        ddl = pickle.loads(s[name + "_ddl"].tobytes())
+        b, r = (int(x) for x in s[name + "_b_r"])
+        keys = [mk(i) for i in range(120)]
+        lsh = dsk.MinHashLSH(threshold=0.8, num_perm=128)
+        assert (lsh.b, lsh.r) == (b, r)
+        for key, row in zip(keys, sig):
+            lsh.insert(key, dsk.LeanMinHash(seed=1, hashvalues=row.astype(np.uint64)))
+        lay = lsh.export_cassandra(b"gpuidx", prepickle=prepickle)
+        assert lay.canonical() == state
+        assert sorted(lay.ddl()) == sorted(ddl) and lay.ddl() == ddl
+        assert lay.keys_table == "lsh_gpuidx_keys" and lay.bucket_tables[1] == "lsh_gpuidx_bucket_0001"
+        # the layout built from explicit band keys (what storage_export.cassandra_layout does after one dsk_band_keys launch)
+        lay2 = se.CassandraLayout(b"gpuidx", b)
+        for key, row in zip(keys, sig):
+            hs = [row[i * r:(i + 1) * r].astype(">u8").tobytes() for i in range(b)]
+            lay2.add(pickle.dumps(key) if prepickle else key, hs)
+        assert lay2 == lay
+        # replay through a driver-style session: the rows land where the reference's code put them
+        from oracle import fake_backends as fb
+        fb.reset()
+        n = lay.write(fb._Session())
+        assert n == sum(len(v) for v in state.values())
+        got = {t: [kv for kv, _ in sorted(rows.items(), key=lambda x: x[1])] for t, rows in fb.CQL["tables"].items()}
+        assert got == state
+    lsh = dsk.MinHashLSH(threshold=0.8, num_perm=128)
+    lsh.insert("not-bytes", dsk.LeanMinHash(seed=1, hashvalues=sig[0].astype(np.uint64)))
+    with pytest.raises(TypeError):
+        lsh.export_cassandra(b"x")                      # prepickle defaults to False for Cassandra: keys must be bytes
+    assert len(lsh.export_cassandra(b"x", prepickle=True).tables["lsh_x_keys"]) == lsh.b
