@@ -431,7 +431,7 @@ def test_jaccard_pairs_and_topk_kernels(emu):
         assert np.array_equal(oc_idx[i], order) and np.array_equal(oc_cnt[i], c[order])
 
 
-@pytest.mark.parametrize("k,n,nq,topk,vals", [(64, 300, 70, 5, 3), (128, 520, 64, 10, 1 << 32), (100, 257, 130, 7, 50), (32, 140, 10, 32, 2)])
+@pytest.mark.parametrize("k,n,nq,topk,vals", [(64, 200, 66, 5, 3), (128, 260, 40, 10, 1 << 32), (100, 257, 70, 7, 50), (32, 140, 10, 32, 2)])
 def test_topk_with_fingerprint_prefilter_equals_exact(emu, k, n, nq, topk, vals):
     """jaccard_topk_pf_kernel: bit-sliced 16-bit fingerprints give an upper bound of the match count; only pairs whose bound
     could still enter the list are counted exactly -- the lists must equal a brute-force ranking (and the exact kernel's):
@@ -505,17 +505,20 @@ def test_wmh_kernel_both_formulas(emu, golden, tag):
         g = golden(name)
         dim, ss, seed = (int(x) for x in g[f"{tag}_cfg"])
         rs_, ln_cs, betas = o.wmh_params(dim, ss, seed)
+        cap = 6                                   # vectors per case: the emulation runs one host thread per CUDA thread
         V = np.ascontiguousarray(g[f"{tag}_X" if many else f"{tag}_v"], dtype=np.float32)
+        V = np.ascontiguousarray(V[:cap])
         out = np.zeros((len(V), ss, 2), dtype=np.int64)
         status = np.zeros(len(V), dtype=np.int32)
         assert lib.emu_wmh(_ptr(np.ascontiguousarray(rs_)), _ptr(np.ascontiguousarray(ln_cs)), _ptr(np.ascontiguousarray(betas)),
                            ss, dim, _ptr(V), ctypes.c_int64(len(V)), _ptr(out), _ptr(status), many) == 0
+        want = g[f"{tag}_out"][:len(V)]
         if many:
-            null = g[f"{tag}_null"]
+            null = g[f"{tag}_null"][:len(V)]
             assert np.array_equal(status.astype(bool), null)
-            assert np.array_equal(out[~null], g[f"{tag}_out"][~null])
+            assert np.array_equal(out[~null], want[~null])
         else:
-            assert not status.any() and np.array_equal(out, g[f"{tag}_out"])
+            assert not status.any() and np.array_equal(out, want)
 
 
 # ---- randomised differential run ---------------------------------------------------------------------------------------
