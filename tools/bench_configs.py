@@ -32,7 +32,7 @@ def ev_time(fn, iters=3, warm=1):
     return e0.elapsed_time(e1) / iters
 
 
-def c3(n_docs, t=128, k=256, n_query=100_000):
+def c3(n_docs, t=128, k=256, n_query=100_000, fused_leg=False):
     """10M x 128 tokens, K=256 + LSH(0.8) insert + query (here n_docs on one GPU)."""
     perms = _make_permutations(k, 1)
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -63,7 +63,7 @@ def c3(n_docs, t=128, k=256, n_query=100_000):
     # indexes, the first one warms the kernel up; candidates of the same queries must be identical to the two-step index
     ms_fused = []
     fused = None
-    for rep in range(3):
+    for rep in range(3 if fused_leg else 0):
         del fused
         fused = dsk.GpuLSH(threshold=0.8, num_perm=k, capacity=n_docs)
         torch.cuda.synchronize()
@@ -73,12 +73,14 @@ def c3(n_docs, t=128, k=256, n_query=100_000):
         torch.cuda.synchronize()
         ms_fused.append(e0.elapsed_time(e1))
     q = sig[torch.randint(0, n_docs, (n_query,), device="cuda", generator=g)]
-    pf, xf = fused.query(q[:20_000], to_host=False)
-    pp, xp = lsh.query(q[:20_000], to_host=False)
-    same = bool(torch.equal(pf, pp)) and bool(torch.equal(
-        torch.sort(xf.long() + torch.repeat_interleave(torch.arange(20_000, device="cuda"), pf[1:] - pf[:-1]) * n_docs)[0],
-        torch.sort(xp.long() + torch.repeat_interleave(torch.arange(20_000, device="cuda"), pp[1:] - pp[:-1]) * n_docs)[0]))
-    del fused
+    same = None
+    if fused_leg:
+        pf, xf = fused.query(q[:20_000], to_host=False)
+        pp, xp = lsh.query(q[:20_000], to_host=False)
+        same = bool(torch.equal(pf, pp)) and bool(torch.equal(
+            torch.sort(xf.long() + torch.repeat_interleave(torch.arange(20_000, device="cuda"), pf[1:] - pf[:-1]) * n_docs)[0],
+            torch.sort(xp.long() + torch.repeat_interleave(torch.arange(20_000, device="cuda"), pp[1:] - pp[:-1]) * n_docs)[0]))
+        del fused
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ptr, idx = lsh.query(q, to_host=False)
@@ -99,7 +101,7 @@ def c3(n_docs, t=128, k=256, n_query=100_000):
     return {"config": "C3 (1 GPU)", "docs": n_docs, "tokens": t, "num_perm": k, "b": lsh.b, "r": lsh.r,
             "signature_ms": ms_sig, "signatures_per_s": n_docs / ms_sig * 1e3,
             "lsh_insert_ms": ms_ins, "lsh_insert_docs_per_s": n_docs / ms_ins * 1e3,
-            "fused_signatures_plus_insert_ms": min(ms_fused[1:]), "fused_runs_ms": ms_fused,
+            "fused_signatures_plus_insert_ms": min(ms_fused[1:]) if ms_fused else None, "fused_runs_ms": ms_fused,
             "two_step_signatures_plus_insert_ms": ms_sig + ms_ins, "fused_candidates_identical": same,
             "lsh_query_ms": ms_q, "queries": n_query, "lsh_queries_per_s": n_query / ms_q * 1e3,
             "candidates_total": int(ptr[-1].item()),
@@ -173,7 +175,12 @@ if __name__ == "__main__":
     ap.add_argument("--c3-docs", type=int, default=2_000_000)
     ap.add_argument("--c4-vecs", type=int, default=20_000)
     ap.add_argument("--c5-rows", type=int, default=100_000)
+    ap.add_argument("--c3-fused", action="store_true",
+                    help="also time GpuLSH.insert_tokens (fused signatures + insert); this leg has not completed a GPU run yet "
+                         "(profiles/README.md r2w_*), tools/diag_fused.py holds the fused timing of record")
     a = ap.parse_args()
-    for fn, arg in ((c3, a.c3_docs), (c4, a.c4_vecs), (c5, a.c5_rows)):
+    if a.c3_docs > 0:
+        print(json.dumps(c3(a.c3_docs, fused_leg=a.c3_fused)), flush=True)
+    for fn, arg in ((c4, a.c4_vecs), (c5, a.c5_rows)):
         if arg > 0:
             print(json.dumps(fn(arg)), flush=True)
