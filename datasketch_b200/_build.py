@@ -33,7 +33,8 @@ def source_hash() -> str:
     """Content hash of everything the library is built from (mtimes do not survive snapshots)."""
     import hashlib
     h = hashlib.sha256()
-    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "dsk.h")]
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
+        os.path.join(HERE, "..", "include", "dsk.h")]   # sources only: a stray directory / cache file in csrc/ is not one
     for d in deps:
         with open(d, "rb") as f:
             h.update(os.path.basename(d).encode() + b"\0" + f.read())
