@@ -791,3 +791,34 @@ def test_fused_lsh_insert_from_tokens_vs_dict_oracle(emu, k, b, r):
         multi += len(got) > 1
     assert multi >= 5            # the planted duplicates really share buckets
     lib.emu_lsh_destroy(h)
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_general_variants_structured_tokens_wraps_and_extreme_parameters(emu, gen):
+    """The general variants on the inputs random data never produces: tiny and near-2^32 low words (L' < 8: the wrap of
+    L' - 8, many exact ties), high words 0 / 1 / 2^32-1, tokens 0 and 2^64-1, and permutations at the ends of their ranges
+    (a = 1, a = p - 1, b = 0, b = p - 1, a with a zero low word) next to ones built to hit the conditional subtract."""
+    rs = np.random.RandomState(gen)
+    lo = np.concatenate([np.arange(0, 1500, dtype=np.uint64), np.uint64(1 << 32) - np.arange(1, 1501, dtype=np.uint64),
+                         np.zeros(250, dtype=np.uint64), np.full(250, 0xFFFFFFFF, dtype=np.uint64)])
+    k = 64
+    perms = _unsafe_perms(k, rs)
+    perms[0, 1], perms[1, 1] = 1, 0
+    perms[0, 2], perms[1, 2] = P61 - 1, P61 - 1
+    perms[0, 4], perms[1, 4] = np.uint64(7 << 32), 5              # a_lo = 0: L' is the same for every token
+    perms[0, 5], perms[1, 5] = 1, P61 - 1                          # x = h + p - 1: the subtract fires for h = 1 .. 8
+    off = np.arange(0, len(lo) + 1, 125, dtype=np.int64)
+    if gen == 2:
+        hi = rs.choice(np.array([0, 1, 0xFFFFFFFF, 0x80000000, 12345], dtype=np.uint64), size=len(lo))
+        tok = (hi << np.uint64(32)) | lo
+        tok[7], tok[130] = np.uint64(0), np.uint64(0xFFFFFFFFFFFFFFFF)
+        want = oc.minhash_bulk_u64tok(tok, off, perms)
+        small = slice(0, 2)                         # the big-int form on the first two documents pins the C oracle here too
+        assert np.array_equal(want[small], _brute(tok[:250], off[:3], perms))
+        assert np.array_equal(emu(tok, off, perms, TWO_PHASE, docs_per_unit=5, grid_x=2), want)
+    else:
+        tok = lo.astype(np.uint32)
+        want = oc.minhash_bulk_u32tok(tok, off, perms)
+        assert np.array_equal(want[:2], _brute(tok[:250], off[:3], perms))
+        assert np.array_equal(emu(tok, off, perms, TWO_PHASE, gen=1, docs_per_unit=5, grid_x=2), want)
+    assert np.array_equal(emu(tok, off, perms, EXACT), want)

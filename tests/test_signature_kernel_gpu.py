@@ -193,3 +193,31 @@ def test_u64_tokens_full_size_properties():
     d_dup = torch.cat([d_tok.view(n, t), d_tok.view(n, t)[:, : t // 2]], dim=1).contiguous().view(-1)
     d_off2 = torch.from_numpy(np.arange(n + 1, dtype=np.int64) * (t + t // 2)).cuda()
     assert torch.equal(dsk.engine.bulk_signatures_device(d_dup, d_off2, d_dup.numel(), P), sig)
+
+
+@pytest.mark.parametrize("u64", [False, True])
+def test_general_variants_structured_tokens_wraps_and_extreme_parameters(u64):
+    """Inputs random data never produces (the same case runs on the CPU emulation): tiny and near-2^32 low words (L' < 8:
+    the wrap of L' - 8, many exact ties), high words 0 / 1 / 2^32-1, tokens 0 and 2^64-1, permutations at the ends of their
+    ranges (a = 1, a = p - 1, b = 0, b = p - 1, a with a zero low word) next to ones built to hit the conditional subtract."""
+    import datasketch_b200 as dsk
+    rs = np.random.RandomState(2 if u64 else 1)
+    lo = np.concatenate([np.arange(0, 1500, dtype=np.uint64), np.uint64(1 << 32) - np.arange(1, 1501, dtype=np.uint64),
+                         np.zeros(250, dtype=np.uint64), np.full(250, 0xFFFFFFFF, dtype=np.uint64)])
+    k = 64
+    perms = _unsafe_perms(k, rs)
+    perms[0, 1], perms[1, 1] = 1, 0
+    perms[0, 2], perms[1, 2] = P61 - 1, P61 - 1
+    perms[0, 4], perms[1, 4] = np.uint64(7 << 32), 5              # a_lo = 0: L' is the same for every token
+    perms[0, 5], perms[1, 5] = 1, P61 - 1                          # x = h + p - 1: the subtract fires for h = 1 .. 8
+    off = np.arange(0, len(lo) + 1, 125, dtype=np.int64)
+    if u64:
+        hi = rs.choice(np.array([0, 1, 0xFFFFFFFF, 0x80000000, 12345], dtype=np.uint64), size=len(lo))
+        tok = (hi << np.uint64(32)) | lo
+        tok[7], tok[130] = np.uint64(0), np.uint64(0xFFFFFFFFFFFFFFFF)
+        want = oc.minhash_bulk_u64tok(tok, off, perms)
+    else:
+        tok = lo.astype(np.uint32)
+        want = oc.minhash_bulk_u32tok(tok, off, perms)
+    for kernel in ("auto", "exact"):
+        assert np.array_equal(dsk.engine.bulk_signatures(tok, off, perms, kernel=kernel), want), kernel
