@@ -126,6 +126,14 @@ def test_minhash_parity_tests_run_on_the_emulated_library(dsk_on_emu, golden):
         t.test_long_documents_are_split_and_merged(dsk, kernel)      # a 2.5M-token document cut into pieces
 
 
+def test_general_variant_gpu_tests_run_on_the_emulated_library(dsk_on_emu):
+    """The host-buffer GPU tests of the general variants (u32 tokens + unsafe permutations, u64 tokens) through the Python
+    layer and the C-ABI on the emulated library: routing (dsk_perm_create's analysis -> BulkParams::gen) included."""
+    import test_signature_kernel_gpu as ts
+    ts.test_general_variants_structured_tokens_wraps_and_extreme_parameters(False)
+    ts.test_general_variants_structured_tokens_wraps_and_extreme_parameters(True)
+
+
 def test_api_fuzz_runs_on_the_emulated_library(dsk_on_emu):
     import test_minhash_gpu as t
     t.test_api_fuzz_against_oracle(dsk_on_emu)
