@@ -77,7 +77,9 @@ static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val) {
     return cmp;
 }
 static inline int atomicCAS(int *p, int cmp, int val) {
+    const int want = cmp;
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    if (cmp != want) sched_yield();   // a failed claim is a spin on a lock another host thread holds: let it run
     return cmp;
 }
 static inline unsigned atomicMin(unsigned *p, unsigned v) {
@@ -222,41 +224,44 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {   // redux.sync
 static inline int __all_sync(unsigned, int pred) { return emu_ballot(pred != 0) == 0xFFFFFFFFu; }
 static inline int __any_sync(unsigned, int pred) { return emu_ballot(pred != 0) != 0u; }
 
-// ---- launch: CTAs run one after the other (the kernels' __shared__ arrays are static), block_threads host threads each
+// ---- launch: CTAs run one after the other (the kernels' __shared__ arrays are static), block_threads host threads that
+// are created ONCE per launch and walk the grid together (a CTA-wide barrier separates consecutive CTAs): launches of
+// hundreds of small CTAs no longer pay a thread creation per CUDA thread and CTA
 #include <thread>
 #include <tuple>
 #include <vector>
 template <typename... KArgs, typename... Args>
 static inline void emu_launch(void (*kernel)(KArgs...), dim3 grid, unsigned block_threads, size_t smem_bytes, Args... args) {
     std::tuple<KArgs...> kargs(static_cast<KArgs>(args)...);
-    for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx) {
-            const unsigned nwarps = (block_threads + 31) / 32;
-            std::vector<EmuWarp> warps(nwarps);
-            for (unsigned w = 0; w < nwarps; ++w) {
-                const unsigned lanes = (w + 1) * 32 <= block_threads ? 32 : block_threads - w * 32;
-                pthread_barrier_init(&warps[w].bar, nullptr, lanes);
-            }
-            std::vector<unsigned char> dyn(smem_bytes + 256);
-            EmuCta cta;
-            pthread_barrier_init(&cta.bar, nullptr, block_threads);
-            cta.dyn_smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~(uintptr_t)127);
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < block_threads; ++t)
-                th.emplace_back([&, t] {
-                    threadIdx = {t, 0, 0};
+    const unsigned nwarps = (block_threads + 31) / 32;
+    std::vector<EmuWarp> warps(nwarps);
+    for (unsigned w = 0; w < nwarps; ++w) {
+        const unsigned lanes = (w + 1) * 32 <= block_threads ? 32 : block_threads - w * 32;
+        pthread_barrier_init(&warps[w].bar, nullptr, lanes);
+    }
+    std::vector<unsigned char> dyn(smem_bytes + 256);
+    EmuCta cta;
+    pthread_barrier_init(&cta.bar, nullptr, block_threads);
+    cta.dyn_smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~(uintptr_t)127);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < block_threads; ++t)
+        th.emplace_back([&, t] {
+            threadIdx = {t, 0, 0};
+            gridDim = {grid.x, grid.y, 1};
+            blockDim = {block_threads, 1, 1};
+            emu_warp = &warps[t >> 5];
+            emu_lane = (int)(t & 31);
+            emu_cta = &cta;
+            for (unsigned by = 0; by < grid.y; ++by)
+                for (unsigned bx = 0; bx < grid.x; ++bx) {
                     blockIdx = {bx, by, 0};
-                    gridDim = {grid.x, grid.y, 1};
-                    blockDim = {block_threads, 1, 1};
-                    emu_warp = &warps[t >> 5];
-                    emu_lane = (int)(t & 31);
-                    emu_cta = &cta;
                     std::apply(kernel, kargs);
-                });
-            for (auto &x : th) x.join();
-            for (auto &w : warps) pthread_barrier_destroy(&w.bar);
-            pthread_barrier_destroy(&cta.bar);
-        }
+                    pthread_barrier_wait(&cta.bar);   // the whole CTA is done before the next one reuses the shared memory
+                }
+        });
+    for (auto &x : th) x.join();
+    for (auto &w : warps) pthread_barrier_destroy(&w.bar);
+    pthread_barrier_destroy(&cta.bar);
 }
 
 // ---- mbarrier + 1-D bulk copies, emulated ADVERSARIALLY --------------------------------------------------------------

@@ -431,7 +431,7 @@ def test_jaccard_pairs_and_topk_kernels(emu):
         assert np.array_equal(oc_idx[i], order) and np.array_equal(oc_cnt[i], c[order])
 
 
-@pytest.mark.parametrize("k,n,nq,topk,vals", [(64, 200, 66, 5, 3), (128, 260, 40, 10, 1 << 32), (100, 257, 70, 7, 50), (32, 140, 10, 32, 2)])
+@pytest.mark.parametrize("k,n,nq,topk,vals", [(64, 200, 66, 5, 3), (128, 260, 40, 10, 1 << 32), (100, 257, 40, 7, 50), (32, 140, 10, 32, 2)])
 def test_topk_with_fingerprint_prefilter_equals_exact(emu, k, n, nq, topk, vals):
     """jaccard_topk_pf_kernel: bit-sliced 16-bit fingerprints give an upper bound of the match count; only pairs whose bound
     could still enter the list are counted exactly -- the lists must equal a brute-force ranking (and the exact kernel's):
@@ -444,7 +444,7 @@ def test_topk_with_fingerprint_prefilter_equals_exact(emu, k, n, nq, topk, vals)
     db[near, : k // 2] = db[rs.randint(0, n, 40), : k // 2]             # half-equal rows
     base = 17
     q = np.ascontiguousarray(db[base:base + nq])
-    for self_base in (base, -1):
+    for self_base in ((base, -1) if k == 64 else (base,)):     # "no self row" once; the emulated CTAs are slow
         got_c = np.zeros((nq, topk), dtype=np.int32)
         got_i = np.zeros((nq, topk), dtype=np.int64)
         assert lib.emu_jaccard_topk_pf(_ptr(q), ctypes.c_int64(nq), _ptr(db), ctypes.c_int64(n), k, topk,
