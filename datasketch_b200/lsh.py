@@ -565,8 +565,15 @@ class GpuLSH:
         the signature kernel builds each row straight into the index's storage and the warp that finishes a row does
         its bucket updates (``dsk_lsh_insert_tokens``).  ``permutations`` is the (2, K) array of ``MinHash.permutations``."""
         import torch
-        if not d_tokens.is_cuda or not d_offsets.is_cuda or d_tokens.device.index != self.device:
+        if not d_tokens.is_cuda or not d_offsets.is_cuda or d_tokens.device.index != self.device \
+                or d_offsets.device.index != self.device:
             raise ValueError("insert_tokens needs CUDA tensors on device %d" % self.device)
+        if d_offsets.dtype != torch.int64 or d_offsets.dim() != 1 or d_offsets.numel() < 1 or not d_offsets.is_contiguous():
+            raise ValueError("offsets must be a contiguous 1-D int64 tensor of length n_docs + 1")
+        if d_tokens.element_size() not in (4, 8) or d_tokens.is_floating_point() or not d_tokens.is_contiguous():
+            raise ValueError("tokens must be a contiguous 32-bit or 64-bit integer tensor")
+        if int(n_tokens) > d_tokens.numel():
+            raise ValueError("n_tokens exceeds the token tensor")
         hp = nv.perm_handle(permutations, self.device)
         if hp.num_perm != self.h:
             raise ValueError("Expecting permutations of length %d, got %d" % (self.h, hp.num_perm))
